@@ -1,0 +1,734 @@
+// pgb_export.cu — host pipeline behind pgb_export_gt_vcf / pgb_export_gt_vcf_mem.
+//
+// Replaces the body loop of Pfile::output_vcf (/root/reference/src/pfile.rs:149-192):
+// instead of one lseek+read per variant and two buffered writes per genotype, the kept
+// variants are cut into contiguous chunks; each chunk's records, prefixes and row indices
+// are staged in page-locked memory, copied H2D in one transfer, indexed (K1), formatted
+// (K2) and copied D2H into a page-locked ring that a writer thread drains to the sink.
+// Contiguous chunk ranges are sharded over the requested devices; no collective is needed
+// because line offsets are a closed-form function of the prefix offsets and K.
+//
+// There is no CPU formatting path in this file: without a CUDA device the calls fail with
+// PGB_E_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "pgb_internal.h"
+
+namespace {
+
+constexpr int kSlots = 3;
+constexpr uint64_t kAlign = 256;
+
+inline uint64_t align_up(uint64_t x, uint64_t a) { return (x + a - 1) / a * a; }
+
+uint64_t env_u64(const char *name, uint64_t dflt) {
+    const char *s = getenv(name);
+    if (!s || !*s) return dflt;
+    char *e = nullptr;
+    unsigned long long v = strtoull(s, &e, 0);
+    return (e && e != s) ? (uint64_t)v : dflt;
+}
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            pgb_set_error("%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);     \
+            return e__ == cudaErrorMemoryAllocation ? PGB_E_NOMEM : PGB_E_CUDA;                      \
+        }                                                                                            \
+    } while (0)
+
+struct Slot {
+    uint8_t *h_in = nullptr, *d_in = nullptr;
+    uint64_t cap_in = 0;
+    uint8_t *h_out = nullptr, *d_out = nullptr;
+    uint64_t cap_out = 0;
+    pgb_line_meta *d_meta = nullptr;
+    void *d_scratch = nullptr;
+    uint64_t cap_lines = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_done = nullptr;
+    bool busy = false; // guarded by DeviceCtx::mu
+};
+
+struct DeviceCtx {
+    int device = -1;
+    Slot slot[kSlots];
+    uint8_t *d_mask = nullptr;
+    uint8_t *h_mask = nullptr;
+    uint32_t *d_kidx = nullptr;
+    uint32_t *d_count = nullptr;
+    uint64_t cap_mask = 0;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    std::mutex mu;
+    std::condition_variable cv;
+};
+
+} // namespace
+
+struct pgb_file {
+    int fd = -1;
+    const uint8_t *image = nullptr;
+    bool image_pinned = false;
+    uint64_t bytes = 0; // file or image size
+    uint32_t M = 0, N = 0, R = 0;
+    std::mutex mu; // one export at a time per handle
+    std::vector<DeviceCtx *> ctx;
+};
+
+namespace {
+
+int parse_header(const uint8_t *h, size_t got, pgb_file *f) {
+    // Order of checks follows Pfile::from_prefix, pfile.rs:44-69.
+    if (got < 2) { pgb_set_error("short read of .pgen header"); return PGB_E_IO; }
+    if (h[0] != 0x6C || h[1] != 0x1B) return PGB_E_MAGIC;
+    if (got < 3) { pgb_set_error("short read of .pgen header"); return PGB_E_IO; }
+    if (h[2] != 0x02) { pgb_set_error("storage mode 0x%02x", h[2]); return PGB_E_MODE; }
+    if (got < 12) { pgb_set_error("short read of .pgen header"); return PGB_E_IO; }
+    f->M = (uint32_t)h[3] | (uint32_t)h[4] << 8 | (uint32_t)h[5] << 16 | (uint32_t)h[6] << 24;
+    f->N = (uint32_t)h[7] | (uint32_t)h[8] << 8 | (uint32_t)h[9] << 16 | (uint32_t)h[10] << 24;
+    if (h[11] != 0x40) { pgb_set_error("header byte 11 = 0x%02x", h[11]); return PGB_E_FLAGS; }
+    f->R = pgb_record_bytes(f->N);
+    return PGB_OK;
+}
+
+void free_slot(Slot &s) {
+    if (s.h_in) cudaFreeHost(s.h_in);
+    if (s.d_in) cudaFree(s.d_in);
+    if (s.h_out) cudaFreeHost(s.h_out);
+    if (s.d_out) cudaFree(s.d_out);
+    if (s.d_meta) cudaFree(s.d_meta);
+    if (s.d_scratch) cudaFree(s.d_scratch);
+    if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+    if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    s = Slot();
+}
+
+void free_ctx(DeviceCtx *c) {
+    if (!c) return;
+    if (cudaSetDevice(c->device) == cudaSuccess) {
+        for (auto &s : c->slot) free_slot(s);
+        if (c->d_mask) cudaFree(c->d_mask);
+        if (c->h_mask) cudaFreeHost(c->h_mask);
+        if (c->d_kidx) cudaFree(c->d_kidx);
+        if (c->d_count) cudaFree(c->d_count);
+        if (c->ev_a) cudaEventDestroy(c->ev_a);
+        if (c->ev_b) cudaEventDestroy(c->ev_b);
+    }
+    delete c;
+}
+
+struct Chunk {
+    uint64_t a, b;       // line range [a, b)
+    uint64_t out_off;    // offset of the chunk in the body
+    uint64_t out_bytes;
+    uint64_t v0, v1;     // covering file rows [v0, v1]
+    bool dense;          // true: stage the covering row range; false: stage kept rows compactly
+    uint64_t in_rows;    // rows staged
+    uint32_t max_pfx;
+};
+
+struct Sink {
+    int fd = -1;
+    bool positional = false; // pwrite at absolute offsets
+    uint64_t base = 0;
+    uint8_t *mem = nullptr;
+    bool mem_pinned = false;
+    // ordered (non-positional) writes
+    std::mutex mu;
+    std::condition_variable cv;
+    uint64_t next_seq = 0;
+};
+
+struct Job {
+    pgb_file *f;
+    const uint32_t *var_idx;
+    uint64_t n_var;
+    const uint32_t *sam_idx; // nullptr => all
+    uint64_t K;
+    const uint8_t *prefix_blob;
+    const uint64_t *prefix_off;
+    Sink *sink;
+    int variant;
+    std::atomic<int> status{PGB_OK};
+    std::mutex err_mu;
+    char err[512] = {0};
+    void fail(int rc) {
+        int expect = PGB_OK;
+        if (status.compare_exchange_strong(expect, rc)) {
+            std::lock_guard<std::mutex> g(err_mu);
+            snprintf(err, sizeof err, "%s", pgb_last_error());
+        }
+    }
+};
+
+struct DeviceWork {
+    DeviceCtx *ctx;
+    std::vector<Chunk> chunks;
+    uint64_t seq_base = 0;
+    double device_ms = 0;
+    uint64_t h2d = 0, d2h = 0, launches = 0;
+};
+
+int ensure_slot(Slot &s, uint64_t need_in, uint64_t need_out, uint64_t need_lines, bool need_h_out) {
+    if (!s.stream) {
+        CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&s.ev_k0));
+        CU(cudaEventCreate(&s.ev_k1));
+        CU(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    }
+    if (need_in > s.cap_in) {
+        if (s.h_in) cudaFreeHost(s.h_in);
+        if (s.d_in) cudaFree(s.d_in);
+        s.h_in = nullptr; s.d_in = nullptr; s.cap_in = 0;
+        uint64_t cap = align_up(need_in + need_in / 8, 1 << 20);
+        CU(cudaHostAlloc((void **)&s.h_in, cap, cudaHostAllocDefault));
+        CU(cudaMalloc((void **)&s.d_in, cap + 64));
+        s.cap_in = cap;
+    }
+    if (need_out > s.cap_out) {
+        if (s.d_out) cudaFree(s.d_out);
+        s.d_out = nullptr;
+        if (s.h_out) cudaFreeHost(s.h_out);
+        s.h_out = nullptr;
+        s.cap_out = 0;
+        uint64_t cap = align_up(need_out + need_out / 8, 1 << 20);
+        CU(cudaMalloc((void **)&s.d_out, cap));
+        s.cap_out = cap;
+    }
+    if (need_h_out && !s.h_out) CU(cudaHostAlloc((void **)&s.h_out, s.cap_out, cudaHostAllocDefault));
+    if (need_lines > s.cap_lines) {
+        if (s.d_meta) cudaFree(s.d_meta);
+        if (s.d_scratch) cudaFree(s.d_scratch);
+        s.d_meta = nullptr; s.d_scratch = nullptr; s.cap_lines = 0;
+        uint64_t cap = need_lines + need_lines / 8 + 1024;
+        CU(cudaMalloc((void **)&s.d_meta, (cap + 1) * sizeof(pgb_line_meta)));
+        CU(cudaMalloc(&s.d_scratch, pgb_dev_index_scratch_bytes(cap)));
+        s.cap_lines = cap;
+    }
+    return PGB_OK;
+}
+
+int read_fully(int fd, uint8_t *dst, uint64_t n, uint64_t off) {
+    while (n) {
+        ssize_t k = pread(fd, dst, n > (1u << 30) ? (1u << 30) : n, (off_t)off);
+        if (k < 0) {
+            if (errno == EINTR) continue;
+            pgb_set_error("pread: %s", strerror(errno));
+            return PGB_E_IO;
+        }
+        if (k == 0) { pgb_set_error("unexpected end of .pgen (read_exact, pfile.rs:170)"); return PGB_E_RANGE; }
+        dst += k; off += (uint64_t)k; n -= (uint64_t)k;
+    }
+    return PGB_OK;
+}
+
+int write_fully(int fd, const uint8_t *src, uint64_t n, bool positional, uint64_t off) {
+    while (n) {
+        size_t want = n > (1u << 30) ? (1u << 30) : (size_t)n;
+        ssize_t k = positional ? pwrite(fd, src, want, (off_t)off) : write(fd, src, want);
+        if (k < 0) {
+            if (errno == EINTR) continue;
+            pgb_set_error("write: %s", strerror(errno));
+            return PGB_E_IO;
+        }
+        src += k; off += (uint64_t)k; n -= (uint64_t)k;
+    }
+    return PGB_OK;
+}
+
+// Stage layout inside h_in/d_in:  [records | pad16 | prefix bytes | prefix_off u64[n+1] | var_row u32[n]]
+struct Stage {
+    uint64_t rec_bytes, pfx_pos, pfx_bytes, off_pos, row_pos, total;
+};
+
+Stage stage_layout(const Job &j, const Chunk &c, bool records_inline) {
+    Stage s;
+    s.rec_bytes = records_inline ? c.in_rows * (uint64_t)j.f->R : 0;
+    uint64_t n = c.b - c.a;
+    s.pfx_pos = align_up(s.rec_bytes + 16, kAlign);
+    s.pfx_bytes = j.prefix_off[c.b] - j.prefix_off[c.a];
+    s.off_pos = align_up(s.pfx_pos + s.pfx_bytes, kAlign);
+    s.row_pos = align_up(s.off_pos + (n + 1) * 8, kAlign);
+    s.total = align_up(s.row_pos + (c.dense ? n * 4 : 0), kAlign);
+    return s;
+}
+
+// Writer side of one device: waits for a chunk's D2H, drains it to the sink, frees the slot.
+struct Pending {
+    int slot;
+    size_t chunk;
+};
+
+void writer_loop(Job *job, DeviceWork *w, std::deque<Pending> *q, std::mutex *qmu, std::condition_variable *qcv,
+                 bool *done) {
+    DeviceCtx *c = w->ctx;
+    cudaSetDevice(c->device);
+    for (;;) {
+        Pending p;
+        {
+            std::unique_lock<std::mutex> lk(*qmu);
+            qcv->wait(lk, [&] { return !q->empty() || *done; });
+            if (q->empty()) return;
+            p = q->front();
+            q->pop_front();
+        }
+        Slot &s = c->slot[p.slot];
+        const Chunk &ch = w->chunks[p.chunk];
+        cudaError_t e = cudaEventSynchronize(s.ev_done);
+        if (e != cudaSuccess) {
+            pgb_set_error("cudaEventSynchronize: %s", cudaGetErrorString(e));
+            job->fail(PGB_E_CUDA);
+        } else if (job->status.load() == PGB_OK) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) w->device_ms += ms;
+            Sink *sk = job->sink;
+            int rc = PGB_OK;
+            if (sk->mem) {
+                if (!sk->mem_pinned) memcpy(sk->mem + ch.out_off, s.h_out, ch.out_bytes);
+            } else if (sk->positional) {
+                rc = write_fully(sk->fd, s.h_out, ch.out_bytes, true, sk->base + ch.out_off);
+            } else {
+                const uint64_t seq = w->seq_base + p.chunk;
+                std::unique_lock<std::mutex> lk(sk->mu);
+                sk->cv.wait(lk, [&] { return sk->next_seq == seq || job->status.load() != PGB_OK; });
+                if (job->status.load() == PGB_OK) rc = write_fully(sk->fd, s.h_out, ch.out_bytes, false, 0);
+                sk->next_seq = seq + 1;
+                sk->cv.notify_all();
+            }
+            if (rc) job->fail(rc);
+        }
+        if (job->status.load() != PGB_OK && !job->sink->mem && !job->sink->positional) {
+            // keep ordered writers from waiting forever on a failed predecessor
+            std::lock_guard<std::mutex> lk(job->sink->mu);
+            job->sink->next_seq = w->seq_base + p.chunk + 1;
+            job->sink->cv.notify_all();
+        }
+        {
+            std::lock_guard<std::mutex> lk(c->mu);
+            s.busy = false;
+        }
+        c->cv.notify_all();
+    }
+}
+
+int run_device_inner(Job *job, DeviceWork *w, std::deque<Pending> &q, std::mutex &qmu, std::condition_variable &qcv) {
+    DeviceCtx *c = w->ctx;
+    pgb_file *f = job->f;
+    CU(cudaSetDevice(c->device));
+    const uint32_t R = f->R;
+    const uint64_t K = job->K;
+    const bool gather = job->sam_idx != nullptr;
+    const bool need_h_out = !(job->sink->mem && job->sink->mem_pinned);
+
+    // ---- K0: keep-mask -> kept-sample index list (once per call and device) ----
+    if (!c->ev_a) {
+        CU(cudaEventCreate(&c->ev_a));
+        CU(cudaEventCreate(&c->ev_b));
+    }
+    // make sure slot 0 has a stream
+    int rc = ensure_slot(c->slot[0], 1, 1, 1, false);
+    if (rc) return rc;
+    if (gather) {
+        const uint64_t n_mask = 4ull * R; // indices into padding bits are legal (pfile.rs:173 only bounds the byte)
+        if (n_mask + 64 > c->cap_mask) {
+            if (c->d_mask) cudaFree(c->d_mask);
+            if (c->h_mask) cudaFreeHost(c->h_mask);
+            if (c->d_kidx) cudaFree(c->d_kidx);
+            c->d_mask = nullptr; c->h_mask = nullptr; c->d_kidx = nullptr; c->cap_mask = 0;
+            CU(cudaMalloc((void **)&c->d_mask, n_mask + 64));
+            CU(cudaHostAlloc((void **)&c->h_mask, n_mask + 64, cudaHostAllocDefault));
+            CU(cudaMalloc((void **)&c->d_kidx, (n_mask + 64) * sizeof(uint32_t)));
+            c->cap_mask = n_mask + 64;
+        }
+        if (!c->d_count) CU(cudaMalloc((void **)&c->d_count, sizeof(uint32_t)));
+        memset(c->h_mask, 0, n_mask);
+        for (uint64_t i = 0; i < K; i++) c->h_mask[job->sam_idx[i]] = 1;
+        cudaStream_t st = c->slot[0].stream;
+        CU(cudaMemcpyAsync(c->d_mask, c->h_mask, n_mask, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(c->ev_a, st));
+        rc = pgb_dev_compact_samples(c->d_mask, (uint32_t)n_mask, c->d_kidx, c->d_count, st);
+        if (rc) return rc;
+        CU(cudaEventRecord(c->ev_b, st));
+        uint32_t cnt = 0;
+        CU(cudaMemcpyAsync(&cnt, c->d_count, sizeof cnt, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
+        w->device_ms += ms;
+        w->launches += 1;
+        w->h2d += n_mask;
+        if (cnt != K) { pgb_set_error("K0 count %u != %llu", cnt, (unsigned long long)K); return PGB_E_CUDA; }
+    }
+
+    for (size_t ci = 0; ci < w->chunks.size(); ci++) {
+        if (job->status.load() != PGB_OK) break;
+        const Chunk &ch = w->chunks[ci];
+        const int si = (int)(ci % kSlots);
+        Slot &s = c->slot[si];
+        {
+            std::unique_lock<std::mutex> lk(c->mu);
+            c->cv.wait(lk, [&] { return !s.busy; });
+            s.busy = true;
+        }
+        const bool rec_direct = f->image && f->image_pinned && ch.dense; // DMA records straight from the image
+        const Stage lay = stage_layout(*job, ch, !rec_direct);
+        const uint64_t n = ch.b - ch.a;
+        const uint64_t rec_dev_bytes = ch.in_rows * (uint64_t)R;
+        const uint64_t d_rec_region = rec_direct ? align_up(rec_dev_bytes + 16, kAlign) : 0;
+        rc = ensure_slot(s, lay.total + d_rec_region, ch.out_bytes + 64, n, need_h_out);
+        if (rc) return rc;
+
+        // -- stage inputs in page-locked memory
+        uint8_t *h = s.h_in;
+        if (!rec_direct) {
+            if (ch.dense) {
+                const uint64_t off = pgb_record_offset(ch.v0, R);
+                if (f->image) memcpy(h, f->image + off, rec_dev_bytes);
+                else if ((rc = read_fully(f->fd, h, rec_dev_bytes, off))) return rc;
+            } else {
+                for (uint64_t i = 0; i < n; i++) {
+                    const uint64_t off = pgb_record_offset(job->var_idx[ch.a + i], R);
+                    if (f->image) memcpy(h + i * R, f->image + off, R);
+                    else if ((rc = read_fully(f->fd, h + i * R, R, off))) return rc;
+                }
+            }
+            memset(h + lay.rec_bytes, 0, 16);
+        }
+        memcpy(h + lay.pfx_pos, job->prefix_blob + job->prefix_off[ch.a], lay.pfx_bytes);
+        memcpy(h + lay.off_pos, job->prefix_off + ch.a, (n + 1) * 8);
+        if (ch.dense) {
+            uint32_t *vr = (uint32_t *)(h + lay.row_pos);
+            if (job->var_idx) for (uint64_t i = 0; i < n; i++) vr[i] = (uint32_t)(job->var_idx[ch.a + i] - ch.v0);
+            else for (uint64_t i = 0; i < n; i++) vr[i] = (uint32_t)i;
+        }
+
+        // -- H2D, K1, K2, D2H on the slot's stream
+        cudaStream_t st = s.stream;
+        uint8_t *d_stage = s.d_in + d_rec_region;
+        const uint8_t *d_records;
+        if (rec_direct) {
+            CU(cudaMemcpyAsync(s.d_in, f->image + pgb_record_offset(ch.v0, R), rec_dev_bytes, cudaMemcpyHostToDevice, st));
+            CU(cudaMemsetAsync(s.d_in + rec_dev_bytes, 0, 16, st));
+            d_records = s.d_in;
+            w->h2d += rec_dev_bytes;
+        } else {
+            d_records = d_stage;
+        }
+        CU(cudaMemcpyAsync(d_stage, h, lay.total, cudaMemcpyHostToDevice, st));
+        w->h2d += lay.total;
+        CU(cudaEventRecord(s.ev_k0, st));
+        rc = pgb_dev_index_lines(ch.dense ? (const uint32_t *)(d_stage + lay.row_pos) : nullptr,
+                                 (const uint64_t *)(d_stage + lay.off_pos), job->prefix_off[ch.a], n, (uint32_t)K, R,
+                                 s.d_meta, s.d_scratch, st);
+        if (rc) return rc;
+        rc = pgb_dev_format_lines(d_records, s.d_meta, n, d_stage + lay.pfx_pos, gather ? c->d_kidx : nullptr, (uint32_t)K,
+                                  ch.max_pfx, s.d_out, job->variant, st);
+        if (rc) return rc;
+        CU(cudaEventRecord(s.ev_k1, st));
+        w->launches += 4;
+        uint8_t *dst = need_h_out ? s.h_out : job->sink->mem + ch.out_off;
+        CU(cudaMemcpyAsync(dst, s.d_out, ch.out_bytes, cudaMemcpyDeviceToHost, st));
+        w->d2h += ch.out_bytes;
+        CU(cudaEventRecord(s.ev_done, st));
+        {
+            std::lock_guard<std::mutex> lk(qmu);
+            q.push_back(Pending{si, ci});
+        }
+        qcv.notify_one();
+    }
+    return PGB_OK;
+}
+
+void run_device(Job *job, DeviceWork *w) {
+    std::deque<Pending> q;
+    std::mutex qmu;
+    std::condition_variable qcv;
+    bool done = false;
+    pgb_clear_error();
+    std::thread writer(writer_loop, job, w, &q, &qmu, &qcv, &done);
+    int rc = run_device_inner(job, w, q, qmu, qcv);
+    if (rc) job->fail(rc);
+    {
+        std::lock_guard<std::mutex> lk(qmu);
+        done = true;
+    }
+    qcv.notify_all();
+    writer.join();
+    // a failed producer may leave ordered writers of later devices waiting
+    if (job->status.load() != PGB_OK && !job->sink->mem && !job->sink->positional) {
+        std::lock_guard<std::mutex> lk(job->sink->mu);
+        job->sink->next_seq = UINT64_MAX;
+        job->sink->cv.notify_all();
+    }
+    if (cudaSetDevice(w->ctx->device) == cudaSuccess) {
+        for (auto &s : w->ctx->slot)
+            if (s.stream) cudaStreamSynchronize(s.stream);
+    }
+}
+
+int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint32_t *sam_idx, uint64_t n_sam,
+                const uint8_t *prefix_blob, const uint64_t *prefix_off, Sink *sink, uint64_t out_cap, uint64_t *out_len,
+                const int *device_ids, int n_devices, pgb_stats *stats) {
+    const auto t_begin = std::chrono::steady_clock::now();
+    pgb_clear_error();
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (!f) return PGB_E_ARG;
+    if (n_var && !prefix_off) { pgb_set_error("prefix_off is NULL"); return PGB_E_ARG; }
+    const uint32_t R = f->R;
+    const uint64_t K = sam_idx ? n_sam : f->N;
+
+    // ---- validation (the reference panics lazily at pfile.rs:170/173; we fail up front) ----
+    if (sam_idx) {
+        for (uint64_t i = 0; i < n_sam; i++) {
+            if ((uint64_t)sam_idx[i] / 4 >= R) { pgb_set_error("sample index %u outside the record", sam_idx[i]); return PGB_E_RANGE; }
+            if (i && sam_idx[i] <= sam_idx[i - 1]) { pgb_set_error("sam_idx must be strictly ascending"); return PGB_E_ARG; }
+        }
+    }
+    if (K > 0xffffffffull / 4) return PGB_E_ARG;
+    if (!var_idx && n_var > f->M) { pgb_set_error("n_var %llu > variants in file %u", (unsigned long long)n_var, f->M); return PGB_E_RANGE; }
+    uint64_t total_pfx = 0;
+    for (uint64_t i = 0; i < n_var; i++) {
+        const uint64_t v = var_idx ? var_idx[i] : i;
+        if (pgb_record_offset(v, R) + R > f->bytes) {
+            pgb_set_error("variant row %llu lies outside the .pgen (read_exact, pfile.rs:170)", (unsigned long long)v);
+            return PGB_E_RANGE;
+        }
+        if (prefix_off[i + 1] < prefix_off[i] || prefix_off[i + 1] - prefix_off[i] > 0x7fffffffull) {
+            pgb_set_error("prefix_off must be ascending");
+            return PGB_E_ARG;
+        }
+    }
+    if (n_var) total_pfx = prefix_off[n_var] - prefix_off[0];
+    if (total_pfx && !prefix_blob) return PGB_E_ARG;
+    const uint64_t fixed = 4ull * K + 1ull;
+    const uint64_t total = total_pfx + n_var * fixed;
+    if (out_len) *out_len = total;
+    if (sink->mem && total > out_cap) return PGB_E_SPACE;
+    if (stats) {
+        stats->n_lines = n_var;
+        stats->n_kept_samples = K;
+        stats->genotypes = n_var * K;
+        stats->bytes_out = total;
+    }
+    if (n_var == 0) return PGB_OK;
+
+    // ---- devices ----
+    int n_avail = 0;
+    if (cudaGetDeviceCount(&n_avail) != cudaSuccess || n_avail <= 0) {
+        cudaGetLastError();
+        pgb_set_error("cudaGetDeviceCount found no device");
+        return PGB_E_NO_DEVICE;
+    }
+    std::vector<int> devs;
+    if (!device_ids || n_devices <= 0) devs.push_back(0);
+    else devs.assign(device_ids, device_ids + n_devices);
+    for (int d : devs)
+        if (d < 0 || d >= n_avail) { pgb_set_error("device %d not present (%d visible)", d, n_avail); return PGB_E_NO_DEVICE; }
+    const int G = (int)devs.size();
+
+    std::lock_guard<std::mutex> file_lock(f->mu);
+    std::vector<DeviceWork> work(G);
+    for (int g = 0; g < G; g++) {
+        DeviceCtx *c = nullptr;
+        for (DeviceCtx *x : f->ctx) if (x->device == devs[g]) c = x;
+        for (int h = 0; h < g; h++) if (devs[h] == devs[g]) { pgb_set_error("duplicate device id"); return PGB_E_ARG; }
+        if (!c) {
+            c = new DeviceCtx();
+            c->device = devs[g];
+            f->ctx.push_back(c);
+        }
+        work[g].ctx = c;
+    }
+
+    // ---- plan: contiguous line ranges per device balanced by output bytes, then chunks ----
+    const uint64_t chunk_out = env_u64("PGB_CHUNK_MB", 256) << 20;
+    const uint64_t chunk_in = env_u64("PGB_CHUNK_IN_MB", 128) << 20;
+    auto out_before = [&](uint64_t i) { return (prefix_off[i] - prefix_off[0]) + i * fixed; };
+    uint64_t seq = 0;
+    uint64_t line = 0;
+    for (int g = 0; g < G; g++) {
+        uint64_t end;
+        if (g == G - 1) end = n_var;
+        else {
+            const uint64_t target = total / G * (g + 1);
+            uint64_t lo = line, hi = n_var;
+            while (lo < hi) { uint64_t mid = (lo + hi) / 2; if (out_before(mid) < target) lo = mid + 1; else hi = mid; }
+            end = lo;
+        }
+        work[g].seq_base = seq;
+        while (line < end) {
+            Chunk c;
+            c.a = line;
+            c.v0 = var_idx ? var_idx[line] : line;
+            uint64_t b = line + 1;
+            uint64_t vmin = c.v0, vmax = c.v0;
+            uint32_t maxp = (uint32_t)(prefix_off[line + 1] - prefix_off[line]);
+            while (b < end) {
+                const uint64_t ob = out_before(b + 1) - out_before(line);
+                if (ob > chunk_out) break;
+                const uint64_t v = var_idx ? var_idx[b] : b;
+                const uint64_t nmin = std::min(vmin, v), nmax = std::max(vmax, v);
+                const uint64_t cover = (nmax - nmin + 1) * R, compact = (b + 1 - line) * (uint64_t)R;
+                if (std::min(cover, compact) > chunk_in) break;
+                if ((nmax - nmin) >= 0xffffffffull) break;
+                vmin = nmin; vmax = nmax;
+                maxp = std::max(maxp, (uint32_t)(prefix_off[b + 1] - prefix_off[b]));
+                b++;
+            }
+            c.b = b;
+            c.v0 = vmin; c.v1 = vmax;
+            const uint64_t cover_rows = vmax - vmin + 1, kept_rows = b - line;
+            c.dense = cover_rows <= 4 * kept_rows && cover_rows * R <= chunk_in + R;
+            c.in_rows = c.dense ? cover_rows : kept_rows;
+            c.out_off = out_before(line);
+            c.out_bytes = out_before(b) - c.out_off;
+            c.max_pfx = maxp;
+            work[g].chunks.push_back(c);
+            seq++;
+            line = b;
+        }
+    }
+
+    Job job;
+    job.f = f; job.var_idx = var_idx; job.n_var = n_var; job.sam_idx = sam_idx; job.K = K;
+    job.prefix_blob = prefix_blob; job.prefix_off = prefix_off; job.sink = sink;
+    job.variant = (int)env_u64("PGB_K2_VARIANT", 0);
+
+    if (G == 1) run_device(&job, &work[0]);
+    else {
+        std::vector<std::thread> th;
+        for (int g = 0; g < G; g++) th.emplace_back(run_device, &job, &work[g]);
+        for (auto &t : th) t.join();
+    }
+    int rc = job.status.load();
+    if (rc != PGB_OK) {
+        pgb_set_error("%s", job.err);
+        return rc;
+    }
+    if (sink->fd >= 0 && sink->positional) {
+        if (lseek(sink->fd, (off_t)(sink->base + total), SEEK_SET) < 0) { pgb_set_error("lseek: %s", strerror(errno)); return PGB_E_IO; }
+    }
+    if (stats) {
+        for (auto &w : work) {
+            stats->device_ms = std::max(stats->device_ms, w.device_ms);
+            stats->bytes_h2d += w.h2d;
+            stats->bytes_d2h += w.d2h;
+            stats->kernel_launches += w.launches;
+            stats->n_chunks += (int32_t)w.chunks.size();
+        }
+        stats->n_devices = G;
+        stats->e2e_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    }
+    return PGB_OK;
+}
+
+bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+} // namespace
+
+extern "C" int pgb_open(const char *pgen_path, pgb_file **out) {
+    pgb_clear_error();
+    if (!pgen_path || !out) return PGB_E_ARG;
+    *out = nullptr;
+    int fd = open(pgen_path, O_RDONLY);
+    if (fd < 0) { pgb_set_error("open %s: %s", pgen_path, strerror(errno)); return PGB_E_IO; }
+    uint8_t h[12];
+    size_t got = 0;
+    while (got < 12) {
+        ssize_t k = pread(fd, h + got, 12 - got, (off_t)got);
+        if (k < 0 && errno == EINTR) continue;
+        if (k <= 0) break;
+        got += (size_t)k;
+    }
+    pgb_file *f = new pgb_file();
+    int rc = parse_header(h, got, f);
+    if (rc) { close(fd); delete f; return rc; }
+    struct stat st;
+    if (fstat(fd, &st) != 0) { pgb_set_error("fstat: %s", strerror(errno)); close(fd); delete f; return PGB_E_IO; }
+    f->fd = fd;
+    f->bytes = (uint64_t)st.st_size;
+    *out = f;
+    return PGB_OK;
+}
+
+extern "C" int pgb_open_mem(const void *image, uint64_t image_bytes, pgb_file **out) {
+    pgb_clear_error();
+    if (!image || !out) return PGB_E_ARG;
+    *out = nullptr;
+    pgb_file *f = new pgb_file();
+    int rc = parse_header((const uint8_t *)image, (size_t)std::min<uint64_t>(image_bytes, 12), f);
+    if (rc) { delete f; return rc; }
+    f->image = (const uint8_t *)image;
+    f->bytes = image_bytes;
+    f->image_pinned = is_pinned(image);
+    *out = f;
+    return PGB_OK;
+}
+
+extern "C" void pgb_dims(const pgb_file *f, uint32_t *n_variants, uint32_t *n_samples, uint32_t *record_bytes) {
+    if (!f) return;
+    if (n_variants) *n_variants = f->M;
+    if (n_samples) *n_samples = f->N;
+    if (record_bytes) *record_bytes = f->R;
+}
+
+extern "C" void pgb_close(pgb_file *f) {
+    if (!f) return;
+    for (DeviceCtx *c : f->ctx) free_ctx(c);
+    if (f->fd >= 0) close(f->fd);
+    delete f;
+}
+
+extern "C" int pgb_export_gt_vcf(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint32_t *sam_idx,
+                                 uint64_t n_sam, const uint8_t *prefix_blob, const uint64_t *prefix_off, int out_fd,
+                                 const int *device_ids, int n_devices, pgb_stats *stats) {
+    if (out_fd < 0) return PGB_E_ARG;
+    Sink sink;
+    sink.fd = out_fd;
+    off_t cur = lseek(out_fd, 0, SEEK_CUR);
+    int fl = fcntl(out_fd, F_GETFL);
+    sink.positional = cur >= 0 && fl >= 0 && !(fl & O_APPEND);
+    sink.base = cur >= 0 ? (uint64_t)cur : 0;
+    return export_impl(f, var_idx, n_var, sam_idx, n_sam, prefix_blob, prefix_off, &sink, 0, nullptr, device_ids,
+                       n_devices, stats);
+}
+
+extern "C" int pgb_export_gt_vcf_mem(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint32_t *sam_idx,
+                                     uint64_t n_sam, const uint8_t *prefix_blob, const uint64_t *prefix_off,
+                                     uint8_t *out_buf, uint64_t out_cap, uint64_t *out_len, const int *device_ids,
+                                     int n_devices, pgb_stats *stats) {
+    if (!out_buf && out_cap) return PGB_E_ARG;
+    Sink sink;
+    static uint8_t dummy;
+    sink.mem = out_buf ? out_buf : &dummy;
+    sink.mem_pinned = out_buf && is_pinned(out_buf);
+    return export_impl(f, var_idx, n_var, sam_idx, n_sam, prefix_blob, prefix_off, &sink, out_cap, out_len, device_ids,
+                       n_devices, stats);
+}

@@ -1,0 +1,199 @@
+// pfile.cpp — see pfile.hpp.
+#include "pfile.hpp"
+
+#include <errno.h>
+#include <fcntl.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <memory>
+
+#include "expr.hpp"
+
+namespace pgb {
+
+namespace {
+
+void write_all(int fd, const char *p, size_t n) {
+    while (n) {
+        ssize_t k = ::write(fd, p, n);
+        if (k < 0) {
+            if (errno == EINTR) continue;
+            throw PfileError{PGB_E_IO, std::string("write: ") + strerror(errno)};
+        }
+        p += k;
+        n -= (size_t)k;
+    }
+}
+
+// str::trim(): the ASCII members of char::is_whitespace.
+bool rust_ws(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\v' || c == '\f' || c == '\r'; }
+
+} // namespace
+
+Pfile Pfile::from_prefix(const std::string &pfile_prefix) {
+    Pfile p;
+    p.pfile_prefix = pfile_prefix;
+    pgb_file *f = nullptr;
+    int rc = pgb_open(p.pgen_path().c_str(), &f); // same checks, same order as pfile.rs:44-69
+    if (rc != PGB_OK) throw PfileError{rc, std::string(pgb_strerror(rc)) + ": " + p.pgen_path() + " " + pgb_last_error()};
+    pgb_dims(f, &p.num_variants, &p.num_samples, nullptr);
+    pgb_close(f);
+    return p;
+}
+
+MetaTable Pfile::pvar_reader() const {
+    try {
+        return MetaTable(pvar_path());
+    } catch (const MetaError &e) {
+        throw PfileError{e.status, e.msg};
+    }
+}
+
+MetaTable Pfile::psam_reader() const {
+    try {
+        return MetaTable(psam_path());
+    } catch (const MetaError &e) {
+        throw PfileError{e.status, e.msg};
+    }
+}
+
+std::vector<uint32_t> filter_metadata(MetaTable &table, const std::optional<std::string> &query) {
+    std::vector<uint32_t> kept;
+    try {
+        table.parse();
+        const size_t n = table.n_rows();
+        if (n > 0xffffffffull) throw PfileError{PGB_E_ARG, "too many rows"};
+        if (!query) { // map_or(true, ..), pfile.rs:321
+            kept.resize(n);
+            for (size_t i = 0; i < n; i++) kept[i] = (uint32_t)i;
+            return kept;
+        }
+        // The reference re-parses the expression for every row (pfile.rs:328), so a bad
+        // expression only surfaces when there is at least one row.
+        std::unique_ptr<Expr> ex;
+        std::vector<std::string_view> row;
+        for (size_t i = 0; i < n; i++) {
+            if (!ex) ex = std::make_unique<Expr>(*query, table.headers());
+            table.row(i, &row);
+            if (ex->eval_boolean(row)) kept.push_back((uint32_t)i);
+        }
+    } catch (const MetaError &e) {
+        throw PfileError{e.status, e.msg};
+    } catch (const ExprError &e) {
+        throw PfileError{PGB_E_EXPR, e.msg};
+    }
+    return kept;
+}
+
+void Pfile::query_metadata(MetaTable &reader, const std::optional<std::string> &query, const std::string &f_string,
+                           int out_fd) const {
+    try {
+        reader.parse();
+        std::unique_ptr<Expr> q, fs;
+        std::vector<std::string_view> row;
+        std::string buf;
+        for (size_t i = 0; i < reader.n_rows(); i++) {
+            reader.row(i, &row);
+            bool keep = true;
+            if (query) {
+                if (!q) q = std::make_unique<Expr>(*query, reader.headers());
+                keep = q->eval_boolean(row);
+            }
+            if (keep) {
+                if (!fs) fs = std::make_unique<Expr>(f_string, reader.headers());
+                buf += fs->eval_string(row);
+                buf.push_back('\n'); // println!, pfile.rs:98
+                if (buf.size() > (1u << 16)) { write_all(out_fd, buf.data(), buf.size()); buf.clear(); }
+            }
+        }
+        write_all(out_fd, buf.data(), buf.size());
+    } catch (const MetaError &e) {
+        throw PfileError{e.status, e.msg};
+    } catch (const ExprError &e) {
+        throw PfileError{PGB_E_EXPR, e.msg};
+    }
+}
+
+VcfPlan Pfile::plan_vcf(const std::optional<std::string> &sam_query, const std::optional<std::string> &var_query) const {
+    VcfPlan plan;
+    try {
+        // read_pvar_header, pfile.rs:110 — panics first when the .pvar has no '#' line
+        MetaTable pvar = pvar_reader();
+        std::string_view comments, column_line;
+        pvar.leading_header(&comments, &column_line);
+        // psam headers + IID column, pfile.rs:111-126
+        MetaTable psam = psam_reader();
+        psam.parse();
+        int iid = -1;
+        for (size_t c = 0; c < psam.n_cols(); c++)
+            if (psam.headers()[c] == "IID") { iid = (int)c; break; }
+        if (iid < 0) throw PfileError{PGB_E_NO_IID, "IID not among the headers of " + psam_path()};
+        plan.var_idx = filter_metadata(pvar, var_query); // pfile.rs:127
+        plan.sam_idx = filter_metadata(psam, sam_query); // pfile.rs:128
+
+        // header, pfile.rs:139-146
+        std::string &h = plan.header;
+        h += "##fileformat=VCFv4.2\n##source=pgen-rs\n";
+        h.append(comments.data(), comments.size());
+        size_t b = 0, e = column_line.size();
+        while (b < e && rust_ws(column_line[b])) b++;
+        while (e > b && rust_ws(column_line[e - 1])) e--;
+        h.append(column_line.data() + b, e - b);
+        h += "\tFORMAT\t";
+        for (size_t k = 0; k < plan.sam_idx.size(); k++) {
+            if (k) h.push_back('\t');
+            std::string_view id = psam.field(plan.sam_idx[k], (size_t)iid);
+            h.append(id.data(), id.size());
+        }
+        h.push_back('\n');
+
+        // line prefixes, pfile.rs:157-161: every field + '\t', then "GT"
+        const size_t nv = plan.var_idx.size(), nc = pvar.n_cols();
+        plan.prefix_off.resize(nv + 1);
+        uint64_t total = 0;
+        for (size_t k = 0; k < nv; k++) {
+            plan.prefix_off[k] = total;
+            for (size_t c = 0; c < nc; c++) total += pvar.field(plan.var_idx[k], c).size() + 1;
+            total += 2;
+        }
+        plan.prefix_off[nv] = total;
+        plan.prefix_blob.resize(total);
+        uint8_t *w = plan.prefix_blob.data();
+        for (size_t k = 0; k < nv; k++) {
+            for (size_t c = 0; c < nc; c++) {
+                std::string_view f = pvar.field(plan.var_idx[k], c);
+                memcpy(w, f.data(), f.size());
+                w += f.size();
+                *w++ = '\t';
+            }
+            *w++ = 'G';
+            *w++ = 'T';
+        }
+    } catch (const MetaError &e) {
+        throw PfileError{e.status, e.msg};
+    }
+    return plan;
+}
+
+void Pfile::output_vcf(const std::optional<std::string> &sam_query, const std::optional<std::string> &var_query,
+                       const std::string &filename, const int *device_ids, int n_devices, pgb_stats *stats) const {
+    VcfPlan plan = plan_vcf(sam_query, var_query);
+    int fd = ::open(filename.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644); // File::create, pfile.rs:136
+    if (fd < 0) throw PfileError{PGB_E_IO, "create " + filename + ": " + strerror(errno)};
+    struct Closer {
+        int fd;
+        ~Closer() { ::close(fd); }
+    } closer{fd};
+    write_all(fd, plan.header.data(), plan.header.size());
+    pgb_file *f = nullptr;
+    int rc = pgb_open(pgen_path().c_str(), &f); // File::open(self.pgen_path()), pfile.rs:149
+    if (rc != PGB_OK) throw PfileError{rc, std::string(pgb_strerror(rc)) + ": " + pgb_last_error()};
+    rc = pgb_export_gt_vcf(f, plan.var_idx.data(), plan.var_idx.size(), plan.sam_idx.data(), plan.sam_idx.size(),
+                           plan.prefix_blob.data(), plan.prefix_off.data(), fd, device_ids, n_devices, stats);
+    std::string detail = pgb_last_error();
+    pgb_close(f);
+    if (rc != PGB_OK) throw PfileError{rc, std::string(pgb_strerror(rc)) + ": " + detail};
+}
+
+} // namespace pgb

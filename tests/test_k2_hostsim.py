@@ -1,0 +1,72 @@
+"""K2's per-lane byte/addressing logic (pgen-rs_b200/csrc/k2_core.cuh) run lane by lane on
+the host and compared with the oracle: every output alignment phase, ragged sample counts,
+gathers, empty selections, multi-tile lines.  This is a CPU pre-check of the kernel source;
+the GPU parity tests are in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import oracle_np as onp
+import synth
+
+VARIANTS = [0x000, 0x010, 0x100, 0x110, 0x200, 0x210, 0x001, 0x002, 0x1000, 0x1110]
+
+
+def run_sim(k2sim, rng, n, m, k_sel, var_sel, plen, phase, variant):
+    r = synth.record_size(n)
+    recs = rng.integers(0, 256, size=(m, r), dtype=np.uint8)
+    flat = np.concatenate([recs.reshape(-1), np.zeros(32, np.uint8)])
+    if var_sel is None:
+        vr, vptr = np.arange(m, dtype=np.uint32), None
+    else:
+        vr = np.sort(rng.choice(m, size=var_sel, replace=False)).astype(np.uint32)
+        vptr = vr.ctypes.data
+    if k_sel is None:
+        ki, sidx, k = None, np.arange(n), n
+    else:
+        sidx = np.sort(rng.choice(n, size=k_sel, replace=False)).astype(np.uint32)
+        k = k_sel
+        ki = np.concatenate([sidx, np.zeros(8, np.uint32)]).astype(np.uint32)
+    pre = [bytes(rng.integers(33, 127, size=rng.integers(plen[0], plen[1] + 1), dtype=np.uint8)) for _ in vr]
+    blob = np.frombuffer(b"".join(pre) + b"\0", dtype=np.uint8).copy()
+    off = np.zeros(len(vr) + 1, np.uint64)
+    off[1:] = np.cumsum([len(x) for x in pre])
+    exp = onp.format_body(recs, vr, sidx, pre)
+    guard = 1024
+    buf = np.full(len(exp) + 2 * guard + 1024, 0xAA, np.uint8)
+    start = guard + (-(buf.ctypes.data + guard)) % 512 + phase
+    k2sim.sim_format_lines(flat.ctypes.data, r, vptr, len(vr), blob.ctypes.data, off.ctypes.data,
+                           None if ki is None else ki.ctypes.data, k, buf.ctypes.data + start, variant)
+    assert buf[start:start + len(exp)].tobytes() == exp
+    assert (buf[:start] == 0xAA).all() and (buf[start + len(exp):] == 0xAA).all(), "wrote outside the body"
+
+
+def test_every_phase_keep_all(k2sim):
+    rng = np.random.default_rng(1)
+    for phase in range(0, 64):
+        run_sim(k2sim, rng, 301, 3, None, None, (0, 37), phase, VARIANTS[phase % len(VARIANTS)])
+
+
+def test_every_phase_gather(k2sim):
+    rng = np.random.default_rng(2)
+    for phase in range(0, 64):
+        run_sim(k2sim, rng, 301, 3, 97, 2, (5, 50), phase, VARIANTS[phase % len(VARIANTS)])
+
+
+def test_random_shapes(k2sim):
+    rng = np.random.default_rng(3)
+    sizes = [1, 2, 3, 4, 5, 7, 8, 15, 16, 17, 31, 33, 63, 64, 65, 100, 127, 129, 300, 511, 1000, 2504, 5000]
+    for _ in range(300):
+        n = int(rng.choice(sizes))
+        m = int(rng.integers(1, 10))
+        k_sel = None if rng.integers(0, 3) == 0 else int(rng.integers(0, n + 1))
+        var_sel = None if rng.integers(0, 2) else int(rng.integers(1, m + 1))
+        plen = [(0, 0), (0, 5), (1, 40), (30, 200)][rng.integers(0, 4)]
+        run_sim(k2sim, rng, n, m, k_sel, var_sel, plen, int(rng.integers(0, 512)), int(rng.choice(VARIANTS)))
+
+
+@pytest.mark.parametrize("n", [20000, 70001])
+def test_wide_lines_span_tiles(k2sim, n):
+    rng = np.random.default_rng(4)
+    for variant in (0, 0x1010, 0x2000, 0x1100):
+        run_sim(k2sim, rng, n, 3, None, None, (10, 60), int(rng.integers(0, 512)), variant)
+        run_sim(k2sim, rng, n, 3, n // 2, 2, (10, 60), int(rng.integers(0, 512)), variant)
