@@ -1,0 +1,416 @@
+"""Parity proper: the CUDA path, called through the C ABI, against the oracle — bit-exact.
+
+Small/medium shapes are compared byte for byte with the oracle; the full BASELINE sizes are
+checked with size-independent properties (decode -> re-encode round trip of every byte on the
+device, closed-form sizes, sampled lines against the oracle)."""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_np as onp
+import synth
+from conftest import ROOT, orc_output_vcf, write_case
+
+pytestmark = pytest.mark.gpu
+CLI = os.path.join(ROOT, "bin", "pgen-b200")
+
+
+def sha(b):
+    return hashlib.sha256(b).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    torch.cuda.set_device(0)
+    return torch
+
+
+def image_of(recs, n):
+    return np.concatenate([np.frombuffer(synth.pgen_header(recs.shape[0], n), dtype=np.uint8), recs.reshape(-1)])
+
+
+def random_prefixes(rng, count, lo, hi):
+    pre = [bytes(rng.integers(33, 127, size=rng.integers(lo, hi + 1), dtype=np.uint8)) for _ in range(count)]
+    blob = np.frombuffer(b"".join(pre) + b"\0", dtype=np.uint8).copy()
+    off = np.zeros(count + 1, np.uint64)
+    off[1:] = np.cumsum([len(x) for x in pre])
+    return pre, blob, off
+
+
+def test_device_present(pgb):
+    assert pgb.lib.pgb_device_count() >= 1
+
+
+def test_golden_vectors_through_pfile_api(pgb, kat_cases, tmp_path):
+    for case in kat_cases:
+        prefix = write_case(case, tmp_path)
+        out = prefix + ".gpu.vcf"
+        pgb.pfile_output_vcf(prefix, case["sam_query"], case["var_query"], out)
+        assert open(out, "rb").read() == case["vcf"].encode(), case["name"]
+
+
+@pytest.mark.parametrize("variant", [0x000, 0x010, 0x100, 0x210, 0x001, 0x002, 0x1110])
+def test_random_shapes_bit_exact(pgb, variant, monkeypatch):
+    monkeypatch.setenv("PGB_K2_VARIANT", str(variant))
+    rng = np.random.default_rng(variant + 5)
+    sizes = [1, 2, 3, 4, 5, 7, 8, 15, 16, 17, 31, 33, 63, 64, 65, 100, 127, 129, 300, 511, 1000, 2504, 5000, 20000]
+    for trial in range(40):
+        n = int(rng.choice(sizes))
+        m = int(rng.integers(1, 40))
+        recs = rng.integers(0, 256, size=(m, synth.record_size(n)), dtype=np.uint8)
+        mode = rng.integers(0, 3)
+        sam = None if mode == 0 else np.sort(rng.choice(n, size=int(rng.integers(0, n + 1)), replace=False)).astype(np.uint32)
+        var = None if rng.integers(0, 2) else np.sort(rng.choice(m, size=int(rng.integers(1, m + 1)), replace=False)).astype(np.uint32)
+        rows = np.arange(m) if var is None else var
+        lo, hi = [(0, 0), (0, 5), (1, 40), (30, 200)][rng.integers(0, 4)]
+        pre, blob, off = random_prefixes(rng, len(rows), lo, hi)
+        with pgb.PgenFile(image=image_of(recs, n)) as f:
+            got = pgb.export_to_bytes(f, var, sam, blob, off)
+        want = onp.format_body(recs, rows, np.arange(n) if sam is None else sam, pre)
+        assert got == want, (variant, trial, n, m)
+
+
+def test_basic1_config1_and_full_export(pgb, orc, basic1, tmp_path):
+    """BASELINE configs[0] (filter) and the full export of data/basic1 (real metadata)."""
+    out = str(tmp_path / "cfg1.vcf")
+    st = pgb.pfile_output_vcf(basic1, 'IID == "NA20900"', 'ALT == "G"', out)
+    assert (st.n_lines, st.n_kept_samples) == (4130, 1)
+    want = str(tmp_path / "cfg1.want.vcf")
+    onp.output_vcf(basic1, 'IID == "NA20900"', 'ALT == "G"', want)
+    assert open(out, "rb").read() == open(want, "rb").read()
+    assert os.path.getsize(out) == 718619
+    out = str(tmp_path / "full.vcf")
+    st = pgb.pfile_output_vcf(basic1, None, None, out)
+    assert st.genotypes == 17784 * 2504 and st.kernel_launches > 0
+    want = str(tmp_path / "full.want.vcf")
+    assert orc_output_vcf(orc, basic1, None, None, want, 2) == 0
+    assert os.path.getsize(out) == 181130024
+    assert sha(open(out, "rb").read()) == sha(open(want, "rb").read())
+
+
+def test_random1_full_export(pgb, orc, random1, tmp_path):
+    """BASELINE configs[1]: 300 samples x 200 000 variants, R = 75 (every load phase)."""
+    out = str(tmp_path / "r1.vcf")
+    st = pgb.pfile_output_vcf(random1, None, None, out)
+    assert st.genotypes == 60_000_000
+    want = str(tmp_path / "r1.want.vcf")
+    assert orc_output_vcf(orc, random1, None, None, want, 2) == 0
+    assert sha(open(out, "rb").read()) == sha(open(want, "rb").read())
+
+
+def test_cli_filter_end_to_end(orc, basic1, tmp_path):
+    out = str(tmp_path / "cli.vcf")
+    r = subprocess.run([CLI, "filter", basic1, "--include-sam", 'IID == "NA20900"', "--include-var", 'ALT == "G"', "-o", out],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    want = str(tmp_path / "cli.want.vcf")
+    onp.output_vcf(basic1, 'IID == "NA20900"', 'ALT == "G"', want)
+    assert open(out, "rb").read() == open(want, "rb").read()
+    # default output name, src/main.rs:121-122
+    r = subprocess.run([CLI, "filter", basic1, "--include-var", 'ID == "rs8100066"'], capture_output=True, text=True)
+    assert r.returncode == 0 and os.path.exists(basic1 + ".pgen-rs.vcf")
+
+
+def test_chunking_slots_and_sinks(pgb, tmp_path, monkeypatch):
+    """Many small chunks (slot reuse), and the three sink kinds: positional file, O_APPEND
+    file and a pipe (ordered writes)."""
+    monkeypatch.setenv("PGB_CHUNK_MB", "1")
+    rng = np.random.default_rng(9)
+    n, m = 1001, 6000
+    recs = rng.integers(0, 256, size=(m, synth.record_size(n)), dtype=np.uint8)
+    pre, blob, off = random_prefixes(rng, m, 20, 60)
+    want = onp.format_body(recs, np.arange(m), np.arange(n), pre)
+    p = str(tmp_path / "c.pgen")
+    synth.write_pgen_bytes(p, recs, n)
+    with pgb.PgenFile(p) as f:
+        out = str(tmp_path / "pos.vcf")
+        fd = os.open(out, os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+        os.write(fd, b"HEADER\n")
+        st = f.export_gt_vcf(None, None, blob, off, fd)
+        assert st.n_chunks > 10
+        assert os.lseek(fd, 0, os.SEEK_CUR) == 7 + len(want)
+        os.write(fd, b"TAIL")
+        os.close(fd)
+        assert open(out, "rb").read() == b"HEADER\n" + want + b"TAIL"
+        out = str(tmp_path / "app.vcf")
+        open(out, "wb").write(b"H\n")
+        fd = os.open(out, os.O_WRONLY | os.O_APPEND)
+        f.export_gt_vcf(None, None, blob, off, fd)
+        os.close(fd)
+        assert open(out, "rb").read() == b"H\n" + want
+        r, w = os.pipe()
+        import threading
+        got = []
+        t = threading.Thread(target=lambda: got.append(os.fdopen(r, "rb").read()))
+        t.start()
+        f.export_gt_vcf(None, None, blob, off, w)
+        os.close(w)
+        t.join()
+        assert got[0] == want
+        # sparse variant selection (per-row staging) and the gather path from a file
+        var = np.sort(rng.choice(m, size=37, replace=False)).astype(np.uint32)
+        sam = np.sort(rng.choice(n, size=100, replace=False)).astype(np.uint32)
+        pre2, blob2, off2 = random_prefixes(rng, len(var), 5, 30)
+        assert pgb.export_to_bytes(f, var, sam, blob2, off2) == onp.format_body(recs, var, sam, pre2)
+
+
+def test_argument_errors(pgb):
+    rng = np.random.default_rng(3)
+    n, m = 9, 4
+    recs = rng.integers(0, 256, size=(m, 3), dtype=np.uint8)
+    pre, blob, off = random_prefixes(rng, 2, 3, 3)
+    with pgb.PgenFile(image=image_of(recs, n)) as f:
+        def status(var, sam):
+            try:
+                pgb.export_to_bytes(f, var, sam, blob, off)
+                return 0
+            except pgb.PgbError as e:
+                return e.status
+        assert status([0, 3], [0, 8]) == 0
+        assert status([0, 4], None) == pgb.E_RANGE          # row past the file: read_exact, pfile.rs:170
+        assert status([0, 1], [0, 12]) == pgb.E_RANGE       # byte past the record: pfile.rs:173
+        assert status([0, 1], [0, 11]) == 0                 # padding bits are readable in the reference
+        assert status([0, 1], [3, 2]) == pgb.E_ARG          # never produced by filter_metadata
+        assert status([0, 1], [2, 2]) == pgb.E_ARG
+        out = np.zeros(4, np.uint8)
+        with pytest.raises(pgb.PgbError) as ei:
+            f.export_gt_vcf_mem([0, 1], None, blob, off, out.ctypes.data, 4)
+        assert ei.value.status == pgb.E_SPACE
+        with pytest.raises(pgb.PgbError) as ei:
+            f.export_gt_vcf_mem([0, 1], None, blob, off, out.ctypes.data, 4, devices=[99])
+        assert ei.value.status == pgb.E_NO_DEVICE
+
+
+def test_k0_k1_synth_device_level(pgb, torch_cuda):
+    torch = torch_cuda
+    rng = np.random.default_rng(12)
+    # K0: keep-mask -> ascending index list
+    for n in [1, 31, 32, 33, 1023, 1024, 1025, 2504, 70001]:
+        for dens in [0.0, 0.1, 0.5, 1.0]:
+            mask = (rng.random(n) < dens).astype(np.uint8) * rng.integers(1, 255, size=n).astype(np.uint8)
+            d_mask = torch.from_numpy(mask).cuda()
+            d_idx = torch.full((n + 8,), 0xFFFF, dtype=torch.int32, device="cuda")
+            d_cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+            assert pgb.lib.pgb_dev_compact_samples(d_mask.data_ptr(), n, d_idx.data_ptr(), d_cnt.data_ptr(), 0) == 0
+            torch.cuda.synchronize()
+            want = np.nonzero(mask)[0]
+            k = int(d_cnt.item())
+            assert k == len(want)
+            got = d_idx.cpu().numpy()
+            assert (got[:k] == want).all() and (got[k:k + 8] == 0).all()
+    # K1: record index + exclusive prefix sum of line lengths
+    for n_lines in [1, 2, 255, 2048, 2049, 100_000]:
+        plen = rng.integers(0, 300, size=n_lines).astype(np.uint64)
+        base = 1000
+        off = np.concatenate([[base], base + np.cumsum(plen)]).astype(np.uint64)
+        rows = np.sort(rng.choice(4 * n_lines, size=n_lines, replace=False)).astype(np.uint32)
+        kk, pitch = 77, 640
+        d_off = torch.from_numpy(off.view(np.int64)).cuda()
+        d_rows = torch.from_numpy(rows.view(np.int32)).cuda()
+        d_meta = torch.zeros((n_lines + 1) * 4, dtype=torch.int64, device="cuda")
+        d_scr = torch.zeros(pgb.lib.pgb_dev_index_scratch_bytes(n_lines) // 8 + 1, dtype=torch.int64, device="cuda")
+        assert pgb.lib.pgb_dev_index_lines(d_rows.data_ptr(), d_off.data_ptr(), base, n_lines, kk, pitch, d_meta.data_ptr(),
+                                           d_scr.data_ptr(), 0) == 0
+        torch.cuda.synchronize()
+        meta = d_meta.cpu().numpy().view(np.uint64).reshape(n_lines + 1, 4)
+        lens = plen + 4 * kk + 1
+        assert (meta[:, 0] == np.concatenate([[0], np.cumsum(lens)])).all()
+        assert (meta[:-1, 1] == rows.astype(np.uint64) * pitch).all()
+        assert (meta[:-1, 2] == off[:-1] - base).all()
+        assert ((meta[:-1, 3] & 0xFFFFFFFF) == plen).all()
+    # synthetic generator: device == numpy
+    for n, rows0, nrows, pitch_pad in [(2504, 0, 300, 0), (5, 7, 64, 3), (300, 100000, 257, 5), (70001, 3, 9, 0)]:
+        r = synth.record_size(n)
+        pitch = r + pitch_pad
+        d = torch.zeros(nrows * pitch, dtype=torch.uint8, device="cuda")
+        assert pgb.lib.pgb_dev_synth_records(d.data_ptr(), pitch, 42, rows0, nrows, n, 0) == 0
+        torch.cuda.synchronize()
+        got = d.cpu().numpy().reshape(nrows, pitch)[:, :r]
+        assert (got == synth.synth_records(42, rows0, nrows, n)).all()
+
+
+def _device_run(pgb, torch, recs_dev, pitch, n, var_rows, kidx_np, blob, off, max_pfx, variant=0):
+    n_lines = len(off) - 1
+    k = n if kidx_np is None else len(kidx_np)
+    total = int(off[-1] - off[0]) + n_lines * (4 * k + 1)
+    d_blob = torch.from_numpy(blob).cuda()
+    d_off = torch.from_numpy(off.view(np.int64)).cuda()
+    d_rows = None if var_rows is None else torch.from_numpy(np.ascontiguousarray(var_rows, dtype=np.uint32).view(np.int32)).cuda()
+    d_kidx = None if kidx_np is None else torch.from_numpy(np.concatenate([kidx_np, np.zeros(8, np.uint32)]).astype(np.uint32).view(np.int32)).cuda()
+    d_meta = torch.zeros((n_lines + 1) * 4, dtype=torch.int64, device="cuda")
+    d_scr = torch.zeros(pgb.lib.pgb_dev_index_scratch_bytes(n_lines) // 8 + 1, dtype=torch.int64, device="cuda")
+    d_out = torch.full((total + 1024,), 0xAA, dtype=torch.uint8, device="cuda")
+    pgb.dev_format(recs_dev, pitch, d_rows, d_blob, d_off, d_kidx, k, max_pfx, d_out, d_meta, d_scr, variant,
+                   torch.cuda.current_stream().cuda_stream, int(off[0]))
+    torch.cuda.synchronize()
+    return d_out, total
+
+
+def test_chr22_shape_full_size_properties(pgb, torch_cuda):
+    """BASELINE configs[2] at full size (2 504 x 1 100 000, keep all): records synthesised on
+    the device, formatted device-resident, then every output byte is checked by a round trip
+    computed with plain torch ops (text -> codes -> re-packed bytes == the input records), and
+    500 sampled lines are compared with the oracle."""
+    torch = torch_cuda
+    n, m, width = 2504, 1_100_000, 40
+    r = synth.record_size(n)
+    recs = torch.zeros(m * r + 64, dtype=torch.uint8, device="cuda")
+    assert pgb.lib.pgb_dev_synth_records(recs.data_ptr(), r, 3, 0, m, n, 0) == 0
+    blob, off = synth.uniform_prefix_blob(m, 0, width)
+    d_out, total = _device_run(pgb, torch, recs, r, n, None, None, blob, off, width)
+    L = width + 4 * n + 1
+    assert total == m * L == 11_062_700_000
+    assert bool((d_out[total:] == 0xAA).all()), "wrote past the end of the body"
+    lines = d_out[:total].view(m, L)
+    d_blob = torch.from_numpy(blob).cuda().view(m, width)
+    step = 50_000
+    lut = torch.full((256, 256), 255, dtype=torch.uint8, device="cuda")
+    for code, txt in enumerate([b"00", b"01", b"11", b".."]):
+        lut[txt[0], txt[1]] = code
+    shifts = torch.tensor([0, 2, 4, 6], dtype=torch.uint8, device="cuda")
+    for a in range(0, m, step):
+        blk = lines[a:a + step]
+        assert torch.equal(blk[:, :width], d_blob[a:a + step])
+        assert bool((blk[:, L - 1] == 10).all())
+        gt = blk[:, width:width + 4 * n].reshape(-1, n, 4)
+        assert bool((gt[:, :, 0] == 9).all()) and bool((gt[:, :, 2] == 47).all())
+        codes = lut[gt[:, :, 1].long(), gt[:, :, 3].long()]
+        assert bool((codes < 4).all())
+        packed = (codes.view(-1, n // 4, 4) << shifts).sum(dim=2, dtype=torch.uint8)
+        assert torch.equal(packed, recs[a * r:(a + blk.shape[0]) * r].view(-1, r))
+    rng = np.random.default_rng(0)
+    pick = np.sort(rng.choice(m, size=500, replace=False))
+    host_recs = recs[:m * r].view(m, r)[torch.from_numpy(pick).cuda()].cpu().numpy()
+    assert (host_recs == np.concatenate([synth.synth_records(3, int(v), 1, n) for v in pick])).all()
+    pre = [bytes(blob[int(off[v]):int(off[v + 1])]) for v in pick]
+    want = onp.format_body(host_recs, np.arange(len(pick)), np.arange(n), pre)
+    got = lines[torch.from_numpy(pick).cuda()].cpu().numpy().tobytes()
+    assert got == want
+
+
+def test_chr22_gather_heavy_full_size(pgb, orc, torch_cuda, tmp_path):
+    """BASELINE configs[3] at full size: K = 250 of 2 504 samples (seed 4a), 550 000 of
+    1 100 000 variants (seed 4b); the whole 0.57 GB body is compared with the C oracle."""
+    torch = torch_cuda
+    n, m = 2504, 1_100_000
+    r = synth.record_size(n)
+    recs = torch.zeros(m * r + 64, dtype=torch.uint8, device="cuda")
+    assert pgb.lib.pgb_dev_synth_records(recs.data_ptr(), r, 3, 0, m, n, 0) == 0
+    torch.cuda.synchronize()
+    pgen = str(tmp_path / "chr22.pgen")
+    with open(pgen, "wb") as f:
+        f.write(synth.pgen_header(m, n))
+        f.write(recs[:m * r].cpu().numpy().tobytes())
+    sam = synth.subset_indices(41, n, 250)
+    var = synth.subset_indices(42, m, 550_000)
+    blob, off = synth.uniform_prefix_blob(m, 0, 48)
+    blob = blob.reshape(m, 48)[var].reshape(-1).copy()
+    off = (np.arange(len(var) + 1, dtype=np.uint64) * np.uint64(48))
+    want_path = str(tmp_path / "want.body")
+    fd = os.open(want_path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+    rc = orc.orc_export_body(pgen.encode(), var.ctypes.data, len(var), sam.ctypes.data, len(sam), blob.ctypes.data,
+                             off.ctypes.data, fd, 2)
+    os.close(fd)
+    assert rc == 0
+    want = open(want_path, "rb").read()
+    assert len(want) == 550_000 * (48 + 1000 + 1)
+    with pgb.PgenFile(pgen) as f:
+        got = pgb.export_to_bytes(f, var, sam, blob, off)
+    assert sha(got) == sha(want)
+    # the same through the device-resident entry points (K0 for the index list)
+    mask = np.zeros(4 * r, np.uint8)
+    mask[sam] = 1
+    d_mask = torch.from_numpy(mask).cuda()
+    d_idx = torch.zeros(4 * r + 8, dtype=torch.int32, device="cuda")
+    d_cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    assert pgb.lib.pgb_dev_compact_samples(d_mask.data_ptr(), 4 * r, d_idx.data_ptr(), d_cnt.data_ptr(), 0) == 0
+    kidx = d_idx.cpu().numpy().view(np.uint32)[:250]
+    assert (kidx == sam).all()
+    d_out, total = _device_run(pgb, torch, recs, r, n, var, kidx, blob, off, 48)
+    assert sha(d_out[:total].cpu().numpy().tobytes()) == sha(want)
+
+
+def test_biobank_shape_wide_lines(pgb, torch_cuda):
+    """BASELINE configs[4] shape (500 000 samples, 2 MB lines spanning 123 tiles) on a block of
+    variants, byte for byte against the oracle, keep-all and a 50 % gather."""
+    torch = torch_cuda
+    n, m = 500_000, 48
+    r = synth.record_size(n)
+    host = synth.synth_records(5, 1000, m, n)
+    recs = torch.zeros(m * r + 64, dtype=torch.uint8, device="cuda")
+    assert pgb.lib.pgb_dev_synth_records(recs.data_ptr(), r, 5, 1000, m, n, 0) == 0
+    torch.cuda.synchronize()
+    assert (recs[:m * r].cpu().numpy().reshape(m, r) == host).all()
+    blob, off = synth.prefix_blob("1000g", range(1000, 1000 + m), 5)
+    pre = [bytes(blob[int(off[i]):int(off[i + 1])]) for i in range(m)]
+    maxp = max(len(p) for p in pre)
+    for variant in (0, 0x2010):
+        d_out, total = _device_run(pgb, torch, recs, r, n, None, None, blob, off, maxp, variant)
+        want = onp.format_body(host, np.arange(m), np.arange(n), pre)
+        assert len(want) == total and sha(d_out[:total].cpu().numpy().tobytes()) == sha(want)
+        assert bool((d_out[total:] == 0xAA).all())
+    sam = synth.subset_indices(51, n, 250_000)
+    d_out, total = _device_run(pgb, torch, recs, r, n, None, sam, blob, off, maxp)
+    assert sha(d_out[:total].cpu().numpy().tobytes()) == sha(onp.format_body(host, np.arange(m), sam, pre))
+    # and through the host pipeline from a memory image
+    with pgb.PgenFile(image=image_of(host, n)) as f:
+        assert sha(pgb.export_to_bytes(f, None, None, blob, off)) == sha(want)
+
+
+def test_offsets_beyond_4gib_use_u64(pgb, orc, tmp_path):
+    """The reference's record offset wraps at 2^32 (pfile.rs:165, u32 multiply).  On a sparse
+    > 4 GiB .pgen the GPU path must agree with the u64 oracle and differ from the faithful one."""
+    n = 500_000
+    r = synth.record_size(n)
+    first, cnt = 34355, 10  # 34360 * 125000 >= 2^32
+    m = first + cnt
+    p = str(tmp_path / "big.pgen")
+    recs = synth.synth_records(5, first, cnt, n)
+    try:
+        with open(p, "wb") as f:
+            f.write(synth.pgen_header(m, n))
+            f.truncate(12 + m * r)
+            f.seek(12 + first * r)
+            f.write(recs.tobytes())
+            # the rows the wrapped offsets land on hold different data
+            f.seek(12 + ((first + 5) * r) % 2**32)
+            f.write(synth.synth_records(6, 0, 5, n).tobytes())
+    except OSError:
+        pytest.skip("no sparse-file support here")
+    if os.stat(p).st_blocks * 512 > 64 * r:
+        pytest.skip("file system did not keep the file sparse")
+    var = np.arange(first, first + cnt, dtype=np.uint32)
+    sam = synth.subset_indices(7, n, 1000)
+    blob, off = synth.prefix_blob("lean", var, 5)
+    outs = {}
+    for name, flags in (("u64", 2), ("u32", 3)):
+        q = str(tmp_path / (name + ".body"))
+        fd = os.open(q, os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+        assert orc.orc_export_body(p.encode(), var.ctypes.data, cnt, sam.ctypes.data, len(sam), blob.ctypes.data,
+                                   off.ctypes.data, fd, flags) == 0
+        os.close(fd)
+        outs[name] = open(q, "rb").read()
+    assert outs["u64"] != outs["u32"]
+    with pgb.PgenFile(p) as f:
+        got = pgb.export_to_bytes(f, var, sam, blob, off)
+    assert got == outs["u64"]
+
+
+def test_multi_device_sharding_matches_single(pgb, monkeypatch):
+    ndev = pgb.lib.pgb_device_count()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs (variant-range sharding across devices)")
+    monkeypatch.setenv("PGB_CHUNK_MB", "4")
+    rng = np.random.default_rng(21)
+    n, m = 2504, 9000
+    recs = synth.synth_records(8, 0, m, n)
+    pre, blob, off = random_prefixes(rng, m, 30, 180)
+    want = onp.format_body(recs, np.arange(m), np.arange(n), pre)
+    with pgb.PgenFile(image=image_of(recs, n)) as f:
+        for devs in ([0, 1], list(range(ndev))):
+            assert pgb.export_to_bytes(f, None, None, blob, off, devices=devs) == want
