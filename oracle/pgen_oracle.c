@@ -88,16 +88,19 @@ uint64_t orc_record_offset(uint64_t var_idx, uint32_t record_size, int faithful_
     return 12u + var_idx * (uint64_t)record_size;
 }
 
-/* 2-bit extract, pfile.rs:172-175. */
-unsigned orc_decode(const unsigned char *record, uint64_t sam_idx) {
+/* 2-bit extract, pfile.rs:172-175.  (static inline twin for the hot loop: an exported
+ * symbol of a -fPIC library is interposable and would not be inlined, which made the
+ * timed baseline several times slower than the release-mode Rust it stands in for.) */
+static inline unsigned decode_(const unsigned char *record, uint64_t sam_idx) {
     uint64_t sample_offset = sam_idx / 4;
     unsigned host_byte = record[sample_offset];
     unsigned in_byte_offset = (unsigned)(sam_idx % 4);
     return (host_byte >> (in_byte_offset * 2)) & 0x3u;
 }
+unsigned orc_decode(const unsigned char *record, uint64_t sam_idx) { return decode_(record, sam_idx); }
 
 /* genotype text, pfile.rs:177-183. */
-const char *orc_gt_text(unsigned code) {
+static inline const char *gt_text_(unsigned code) {
     switch (code) {
     case 0: return "0/0";
     case 1: return "0/1";
@@ -105,6 +108,7 @@ const char *orc_gt_text(unsigned code) {
     default: return "./.";
     }
 }
+const char *orc_gt_text(unsigned code) { return gt_text_(code); }
 
 /* --------------------------------------------------------- metadata files -- */
 
@@ -288,7 +292,10 @@ static void bw_flush(bufwriter *w) {
     w->n = 0;
 }
 
-static inline void bw_write(bufwriter *w, const void *p, size_t len) {
+/* BufWriter::write: the common case (the bytes fit in the spare capacity) is a plain copy,
+ * inlined so that the constant-length appends of pfile.rs:186-187 become direct stores, as
+ * they do in release-mode Rust; everything else goes through the out-of-line slow path. */
+static __attribute__((noinline)) void bw_write_slow(bufwriter *w, const void *p, size_t len) {
     if (w->n + len > BW_CAP) bw_flush(w);
     if (len >= BW_CAP) {
         const unsigned char *q = (const unsigned char *)p;
@@ -306,6 +313,15 @@ static inline void bw_write(bufwriter *w, const void *p, size_t len) {
     }
     memcpy(w->buf + w->n, p, len);
     w->n += len;
+}
+
+static inline __attribute__((always_inline)) void bw_write(bufwriter *w, const void *p, size_t len) {
+    if (__builtin_expect(w->n + len < BW_CAP, 1)) {
+        memcpy(w->buf + w->n, p, len);
+        w->n += len;
+    } else {
+        bw_write_slow(w, p, len);
+    }
 }
 
 /* ----------------------------------------------------------- output_vcf -- */
@@ -436,7 +452,7 @@ int orc_output_vcf(const char *prefix, const int64_t *var_idx, int64_t n_var, co
                 unsigned char *q = linebuf;
                 for (int64_t j = 0; j < ns; j++) {
                     int64_t s = n_sam < 0 ? j : sam_idx[j];
-                    const char *gt = orc_gt_text(orc_decode(rec, (uint64_t)s));
+                    const char *gt = gt_text_(decode_(rec, (uint64_t)s));
                     q[0] = '\t'; q[1] = (unsigned char)gt[0]; q[2] = (unsigned char)gt[1]; q[3] = (unsigned char)gt[2];
                     q += 4;
                 }
@@ -496,7 +512,7 @@ int orc_export_body(const char *pgen_path, const uint32_t *var_idx, uint64_t n_v
                 for (uint64_t j = 0; j < ns; j++) {
                     uint64_t s = sam_idx ? sam_idx[j] : j;
                     if (s / 4 >= R) { rc = ORC_E_RANGE; break; }
-                    const char *gt = orc_gt_text(orc_decode(rec, s));
+                    const char *gt = gt_text_(decode_(rec, s));
                     bw_write(w, "\t", 1);
                     bw_write(w, gt, 3);
                 }
@@ -505,7 +521,7 @@ int orc_export_body(const char *pgen_path, const uint32_t *var_idx, uint64_t n_v
                 for (uint64_t j = 0; j < ns; j++) {
                     uint64_t s = sam_idx ? sam_idx[j] : j;
                     if (s / 4 >= R) { rc = ORC_E_RANGE; break; }
-                    const char *gt = orc_gt_text(orc_decode(rec, s));
+                    const char *gt = gt_text_(decode_(rec, s));
                     q[0] = '\t'; q[1] = (unsigned char)gt[0]; q[2] = (unsigned char)gt[1]; q[3] = (unsigned char)gt[2];
                     q += 4;
                 }
@@ -532,7 +548,7 @@ uint64_t orc_format_gt_fields(const unsigned char *record, const uint32_t *sam_i
     uint64_t ns = sam_idx ? n_sam : num_samples;
     for (uint64_t j = 0; j < ns; j++) {
         uint64_t s = sam_idx ? sam_idx[j] : j;
-        const char *gt = orc_gt_text(orc_decode(record, s));
+        const char *gt = gt_text_(decode_(record, s));
         out[4 * j] = '\t';
         memcpy(out + 4 * j + 1, gt, 3);
     }

@@ -505,6 +505,9 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
         }
     }
     if (K > 0xffffffffull / 4) return PGB_E_ARG;
+    // A strictly ascending list of N indices ending at N-1 is the identity (what
+    // filter_metadata returns for a None query, pfile.rs:321): take the keep-all path.
+    if (sam_idx && n_sam == f->N && n_sam > 0 && sam_idx[n_sam - 1] == f->N - 1) sam_idx = nullptr;
     if (!var_idx && n_var > f->M) { pgb_set_error("n_var %llu > variants in file %u", (unsigned long long)n_var, f->M); return PGB_E_RANGE; }
     uint64_t total_pfx = 0;
     for (uint64_t i = 0; i < n_var; i++) {

@@ -189,7 +189,10 @@ void Pfile::output_vcf(const std::optional<std::string> &sam_query, const std::o
     pgb_file *f = nullptr;
     int rc = pgb_open(pgen_path().c_str(), &f); // File::open(self.pgen_path()), pfile.rs:149
     if (rc != PGB_OK) throw PfileError{rc, std::string(pgb_strerror(rc)) + ": " + pgb_last_error()};
-    rc = pgb_export_gt_vcf(f, plan.var_idx.data(), plan.var_idx.size(), plan.sam_idx.data(), plan.sam_idx.size(),
+    // an empty std::vector may hand out nullptr, which the C ABI reads as "all samples"
+    static const uint32_t no_samples[1] = {0};
+    const uint32_t *sam = plan.sam_idx.empty() ? no_samples : plan.sam_idx.data();
+    rc = pgb_export_gt_vcf(f, plan.var_idx.data(), plan.var_idx.size(), sam, plan.sam_idx.size(),
                            plan.prefix_blob.data(), plan.prefix_off.data(), fd, device_ids, n_devices, stats);
     std::string detail = pgb_last_error();
     pgb_close(f);

@@ -182,7 +182,8 @@ def test_argument_errors(pgb):
             f.export_gt_vcf_mem([0, 1], None, blob, off, out.ctypes.data, 4)
         assert ei.value.status == pgb.E_SPACE
         with pytest.raises(pgb.PgbError) as ei:
-            f.export_gt_vcf_mem([0, 1], None, blob, off, out.ctypes.data, 4, devices=[99])
+            big = np.zeros(4096, np.uint8)
+            f.export_gt_vcf_mem([0, 1], None, blob, off, big.ctypes.data, big.nbytes, devices=[99])
         assert ei.value.status == pgb.E_NO_DEVICE
 
 
