@@ -110,6 +110,13 @@ int pgb_export_gt_vcf_mem(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, 
                           uint64_t n_sam, const uint8_t *prefix_blob, const uint64_t *prefix_off, uint8_t *out_buf,
                           uint64_t out_cap, uint64_t *out_len, const int *device_ids, int n_devices, pgb_stats *stats);
 
+/* The multi-GPU partition pgb_export_gt_vcf uses: the kept-variant list cut into n_shards
+ * contiguous ranges balanced by output bytes.  line_begin (n_shards+1 entries) receives the
+ * range boundaries, byte_begin (optional, n_shards+1) the body offset at which each range
+ * starts; shard g owns lines [line_begin[g], line_begin[g+1]).  CPU only. */
+int pgb_shard_plan(uint64_t n_var, uint64_t n_kept_samples, const uint64_t *prefix_off, int n_shards,
+                   uint64_t *line_begin, uint64_t *byte_begin);
+
 /* Body size in bytes for the given selection: sum(P_i) + n_var * (4K + 1). */
 uint64_t pgb_body_bytes(uint64_t n_var, uint64_t n_kept_samples, const uint64_t *prefix_off);
 

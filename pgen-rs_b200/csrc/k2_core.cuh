@@ -6,25 +6,31 @@
 //
 // What it replaces: the per-variant loop body of Pfile::output_vcf,
 // /root/reference/src/pfile.rs:156-192 —
-//   :157-161 prefix fields + "GT"       -> head bytes copied from prefix_blob
+//   :157-161 prefix fields + "GT"       -> prefix bytes copied from prefix_blob
 //   :165-170 record offset/seek/read    -> meta.rec_off (device record index from K1)
 //   :171-175 per-sample 2-bit extract   -> body chunks (keep-all: two row bytes per 16 B
 //                                          of text; gather: kidx lookups)
-//   :177-188 code -> "\t0/0" ...        -> gt_word() via two PRMTs (or a smem LUT)
+//   :177-188 code -> "\t0/0" ...        -> shared-memory LUT: record byte -> 4 text words
 //   :190     "\n"                       -> tail bytes
 //
 // Geometry of one output line at absolute address a_ls (P = prefix bytes, K kept samples):
 //   [a_ls, a_gs)  prefix      a_gs = a_ls + P
 //   [a_gs, a_ge)  GT text     a_ge = a_gs + 4K      (field f at a_gs + 4f: '\t' x '/' y)
 //   [a_ge, a_le)  '\n'        a_le = a_ge + 1
-// The warp writes   head = [a_ls, b0)   byte stores   (b0 = align_up(a_gs, 16))
-//                   body = [b0, b1)     16-byte stores, 512 B per warp instruction, every
-//                                       chunk wholly inside the GT text
-//                   tail = [b1, a_le)   byte stores   (b1 = align_down(a_ge, 16))
+// The warp writes   [a_ls, a_gs)  prefix, byte stores
+//                   [a_gs, b0)    <= 15 bytes of GT text, byte stores (b0 = align_up(a_gs, 16))
+//                   body = [b0, b1)  16-byte stores, 512 B per warp instruction, every chunk
+//                                    wholly inside the GT text
+//                   [b1, a_le)    <= 15 bytes of GT text + '\n' (b1 = align_down(a_ge, 16))
 // so every output byte has exactly one writer and no padding is ever emitted (the VCF
 // must be bit-exact).  For a 16-byte chunk at A:  q = A - a_gs, field f0 = q >> 2, byte
 // phase r = q & 3; (q & 15) is the same for every chunk of a line, so in the keep-all
 // case the chunk needs row bytes (q >> 4) and (q >> 4) + 1 shifted by a per-line constant.
+//
+// Instruction budget (round 1 ncu: the first version was ALU-bound at ~100 instructions per
+// 16-byte chunk): the chunk body is  2 LDG.U8, PRMT+SHF (the 10 code bits w), LOP+IMAD+
+// LDS.128 (4 text words from the LUT), SHF+LOP+IMAD+LDS.32 (the 5th word), 4 SHF (byte
+// re-phasing), STG.128 — with full rows unrolled without predicates.
 #pragma once
 #include <stdint.h>
 
@@ -40,7 +46,9 @@ struct pgb_k2_params {
     uint32_t K;
     uint32_t n_tiles;    // tiles per line
     uint32_t tile_bytes; // multiple of 512
-    int store_hint;      // 0 default, 1 .cs (streaming), 2 L1::no_allocate
+    // grid-stride of the (line, tile) items, pre-divided on the host: stride = dl * n_tiles + dt
+    uint64_t stride_lines;
+    uint32_t stride_tiles;
 };
 
 struct pgb_u4 {
@@ -71,7 +79,8 @@ PGB_DEV void pgb_st16(uint64_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w
     uint32_t t[4] = {x, y, z, w};
     memcpy((void *)(uintptr_t)a, t, 16);
 }
-PGB_DEV pgb_u4 pgb_lds_lut(const pgb_u4 *lut, uint32_t i) { return lut[i]; }
+PGB_DEV pgb_u4 pgb_lds4(const pgb_u4 *e) { return *e; }
+PGB_DEV uint32_t pgb_lds1(const uint32_t *e) { return *e; }
 #else
 #define PGB_DEV __device__ __forceinline__
 PGB_DEV uint32_t pgb_prmt(uint32_t x, uint32_t y, uint32_t s) { return __byte_perm(x, y, s); }
@@ -100,11 +109,12 @@ PGB_DEV void pgb_st16(uint64_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w
         asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
     }
 }
-PGB_DEV pgb_u4 pgb_lds_lut(const pgb_u4 *lut, uint32_t i) {
-    uint4 v = *reinterpret_cast<const uint4 *>(lut + i);
+PGB_DEV pgb_u4 pgb_lds4(const pgb_u4 *e) {
+    uint4 v = *reinterpret_cast<const uint4 *>(e);
     pgb_u4 r = {v.x, v.y, v.z, v.w};
     return r;
 }
+PGB_DEV uint32_t pgb_lds1(const uint32_t *e) { return *e; }
 #endif
 
 // Little-endian text word of one genotype field: '\t', a, '/', b  (pfile.rs:177-188).
@@ -130,26 +140,51 @@ PGB_DEV pgb_u4 pgb_lut_entry(uint32_t byte) {
 // 2-bit code of sample s in a record (pfile.rs:172-175).
 PGB_DEV uint32_t pgb_code(const uint8_t *row, uint32_t s) { return (pgb_ld8(row + (s >> 2)) >> ((s & 3u) * 2u)) & 3u; }
 
-// Byte `pos` of a line (generic, used for head/tail only).
+// One byte of the GT region: g = offset from a_gs (g == 4K is the newline).  Used only for
+// the <= 15 + 16 bytes around the 16-byte-aligned body (or for whole lines too short to have one).
 template <bool GATHER>
-PGB_DEV uint32_t pgb_line_byte(const pgb_k2_params &p, const uint8_t *row, const uint8_t *pfx, uint32_t P, uint64_t K4,
-                               uint64_t pos) {
-    if (pos < P) return pgb_ld8(pfx + pos);
-    uint64_t g = pos - P;
+PGB_DEV uint32_t pgb_gt_byte(const pgb_k2_params &p, const uint8_t *row, uint64_t K4, uint64_t g) {
     if (g >= K4) return '\n';
-    uint32_t ch = (uint32_t)g & 3u;
-    if (ch == 0u) return '\t';
-    if (ch == 2u) return '/';
-    uint32_t f = (uint32_t)(g >> 2);
-    uint32_t s = GATHER ? pgb_ld32(p.kidx + f) : f;
-    uint32_t c = pgb_code(row, s);
-    if (c == 3u) return '.';
-    if (ch == 1u) return c == 2u ? '1' : '0';
-    return c == 0u ? '0' : '1';
+    const uint32_t f = (uint32_t)(g >> 2);
+    const uint32_t s = GATHER ? pgb_ld32(p.kidx + f) : f;
+    return (pgb_gt_word(pgb_code(row, s)) >> (((uint32_t)g & 3u) * 8u)) & 0xFFu;
 }
 
-template <bool GATHER, int UNROLL, bool LUT>
-PGB_DEV void pgb_k2_item(const pgb_k2_params &p, uint64_t line, uint32_t tile, uint32_t lane, const pgb_u4 *lut) {
+// Shared-memory table (built once per CTA by the kernel, per call by the host simulation):
+//   lut4[byte * REPL + g]   the four text words of a packed record byte; REPL interleaved copies
+//                           so that the 8 lanes of a quarter-warp (the unit of an LDS.128) can each
+//                           use copy g = lane & (REPL-1) and never collide on a bank (REPL = 8).
+// `l4` is the lane's view of it (lut4 + g).  w holds the chunk's 10 code bits (5 fields): bits
+// 0-7 index the table; of the 5th field only '\t', its first character and '/' can fall
+// inside the chunk (byte phase r <= 3), so its word comes from one PRMT on the table
+// {'0','0','1','.'} | {'\t','/'} instead of a second lookup.
+template <int REPL>
+PGB_DEV void pgb_emit_chunk(uint64_t A, uint32_t w, uint32_t r8, const pgb_u4 *l4, int hint) {
+    const pgb_u4 e = pgb_lds4(l4 + (w & 0xFFu) * REPL);
+    const uint32_t W4 = pgb_prmt(0x2E313030u, 0x00002F09u, ((w >> 4) & 0x30u) | 0x0504u);
+    pgb_st16(A, pgb_funnel_r(e.x, e.y, r8), pgb_funnel_r(e.y, e.z, r8), pgb_funnel_r(e.z, e.w, r8),
+             pgb_funnel_r(e.w, W4, r8), hint);
+}
+
+// The 10 code bits (5 fields) of a 16-byte chunk.  Keep-all: `src` points at the record byte
+// holding the chunk's first field (row + (q >> 4)), sh = 2-bit phase.  Gather: `src` points at
+// the chunk's first kept-sample index (kidx + (q >> 2); kidx is padded by 8 entries).
+template <bool GATHER>
+PGB_DEV uint32_t pgb_chunk_codes(const uint8_t *row, const void *src, uint32_t sh) {
+    if (!GATHER) {
+        const uint8_t *b = (const uint8_t *)src;
+        return pgb_prmt(pgb_ld8(b), pgb_ld8(b + 1), 0x1140u) >> sh;
+    }
+    const uint32_t *ki = (const uint32_t *)src;
+    const uint32_t s0 = pgb_ld32(ki), s1 = pgb_ld32(ki + 1), s2 = pgb_ld32(ki + 2), s3 = pgb_ld32(ki + 3);
+    const uint32_t s4 = pgb_ld32(ki + 4);
+    return pgb_code(row, s0) | (pgb_code(row, s1) << 2) | (pgb_code(row, s2) << 4) | (pgb_code(row, s3) << 6) |
+           (pgb_code(row, s4) << 8);
+}
+
+template <bool GATHER, int HINT, int REPL>
+PGB_DEV void pgb_k2_item(const pgb_k2_params &p, uint64_t line, uint32_t tile, uint32_t lane, const pgb_u4 *lut4) {
+    constexpr int UNROLL = 4;
     const pgb_line_meta m = pgb_ld_meta(p.meta + line);
     const uint32_t P = m.pfx_len;
     const uint64_t K4 = 4ull * p.K;
@@ -161,17 +196,21 @@ PGB_DEV void pgb_k2_item(const pgb_k2_params &p, uint64_t line, uint32_t tile, u
     if (t0 >= a_le) return;
     const uint64_t t1 = t0 + p.tile_bytes;
     uint64_t b0 = (a_gs + 15ull) & ~15ull, b1 = a_ge & ~15ull;
-    if (b0 >= b1) { b0 = a_le; b1 = a_le; }
+    if (b0 >= b1) { b0 = a_le; b1 = a_le; } // no aligned chunk inside the GT text: bytes only
     const uint8_t *row = p.records + m.rec_off;
-    const uint8_t *pfx = p.prefix_blob + m.pfx_off;
 
-    { // head: prefix (+ up to 15 bytes of GT text, or the whole line when there is no body)
-        const uint64_t lo = a_ls > t0 ? a_ls : t0, hi = b0 < t1 ? b0 : t1;
-        for (uint64_t a = lo + lane; a < hi; a += 32) pgb_st8(a, pgb_line_byte<GATHER>(p, row, pfx, P, K4, a - a_ls));
+    { // prefix bytes (pfile.rs:157-161)
+        const uint8_t *pfx = p.prefix_blob + m.pfx_off;
+        const uint64_t lo = a_ls > t0 ? a_ls : t0, hi = a_gs < t1 ? a_gs : t1;
+        for (uint64_t a = lo + lane; a < hi; a += 32) pgb_st8(a, pgb_ld8(pfx + (a - a_ls)));
     }
-    { // tail: last partial chunk of GT text + '\n'
+    { // GT bytes in front of the first aligned chunk
+        const uint64_t lo = a_gs > t0 ? a_gs : t0, hi = b0 < t1 ? b0 : t1;
+        for (uint64_t a = lo + lane; a < hi; a += 32) pgb_st8(a, pgb_gt_byte<GATHER>(p, row, K4, a - a_gs));
+    }
+    { // GT bytes behind the last aligned chunk, and the newline (pfile.rs:190)
         const uint64_t lo = b1 > t0 ? b1 : t0, hi = a_le < t1 ? a_le : t1;
-        for (uint64_t a = lo + lane; a < hi; a += 32) pgb_st8(a, pgb_line_byte<GATHER>(p, row, pfx, P, K4, a - a_ls));
+        for (uint64_t a = lo + lane; a < hi; a += 32) pgb_st8(a, pgb_gt_byte<GATHER>(p, row, K4, a - a_gs));
     }
     const uint64_t lo = b0 > t0 ? b0 : t0, hi = b1 < t1 ? b1 : t1;
     if (lo >= hi) return;
@@ -179,44 +218,25 @@ PGB_DEV void pgb_k2_item(const pgb_k2_params &p, uint64_t line, uint32_t tile, u
     const uint32_t delta = (uint32_t)(0ull - a_gs) & 15u; // (A - a_gs) & 15 for any 16-aligned A
     const uint32_t r8 = (delta & 3u) * 8u;                // byte phase inside a field, in bits
     const uint32_t sh = (delta >> 2) * 2u;                // 2-bit phase inside a record byte
-    for (uint64_t A = (lo & ~511ull) + (uint64_t)lane * 16u; A < hi; A += 512ull * UNROLL) {
-        uint32_t w[UNROLL];
-        bool ok[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            const uint64_t Au = A + 512ull * u;
-            ok[u] = Au >= lo && Au < hi;
-            w[u] = 0;
-            if (ok[u]) {
-                const uint64_t q = Au - a_gs;
-                if (!GATHER) {
-                    const uint8_t *b = row + (q >> 4);
-                    w[u] = (pgb_ld8(b) | (pgb_ld8(b + 1) << 8)) >> sh;
-                } else {
-                    const uint32_t *ki = p.kidx + (q >> 2);
-                    uint32_t s0 = pgb_ld32(ki), s1 = pgb_ld32(ki + 1), s2 = pgb_ld32(ki + 2), s3 = pgb_ld32(ki + 3);
-                    uint32_t s4 = pgb_ld32(ki + 4); // kidx is padded by 8 entries
-                    w[u] = pgb_code(row, s0) | (pgb_code(row, s1) << 2) | (pgb_code(row, s2) << 4) |
-                           (pgb_code(row, s3) << 6) | (pgb_code(row, s4) << 8);
-                }
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            if (!ok[u]) continue;
-            uint32_t W0, W1, W2, W3;
-            if (LUT) {
-                pgb_u4 e = pgb_lds_lut(lut, w[u] & 0xFFu);
-                W0 = e.x; W1 = e.y; W2 = e.z; W3 = e.w;
-            } else {
-                W0 = pgb_gt_word(w[u] & 3u);
-                W1 = pgb_gt_word((w[u] >> 2) & 3u);
-                W2 = pgb_gt_word((w[u] >> 4) & 3u);
-                W3 = pgb_gt_word((w[u] >> 6) & 3u);
-            }
-            const uint32_t W4 = pgb_gt_word((w[u] >> 8) & 3u);
-            pgb_st16(A + 512ull * u, pgb_funnel_r(W0, W1, r8), pgb_funnel_r(W1, W2, r8), pgb_funnel_r(W2, W3, r8),
-                     pgb_funnel_r(W3, W4, r8), p.store_hint);
-        }
+    const pgb_u4 *l4 = lut4 + (lane & (uint32_t)(REPL - 1));
+
+    uint64_t rowA = lo & ~511ull;             // warp-uniform: start of the current 512-byte output row
+    uint64_t A = rowA + (uint64_t)lane * 16u; // this lane's chunk in it
+    // source of the chunk's codes; one output row further = 32 record bytes / 128 kept samples
+    constexpr uint32_t STEP = GATHER ? 128u * 4u : 32u;
+    const int64_t q0 = (int64_t)(A - a_gs);   // may be negative only for a chunk that is skipped
+    const uint8_t *src = GATHER ? (const uint8_t *)p.kidx + (q0 >> 2) * 4 : row + (q0 >> 4);
+    if (rowA < lo) { // the first row starts in front of the body
+        if (A >= lo && A < hi) pgb_emit_chunk<REPL>(A, pgb_chunk_codes<GATHER>(row, src, sh), r8, l4, HINT);
+        rowA += 512; A += 512; src += STEP;
     }
+    for (; rowA + 512ull * UNROLL <= hi; rowA += 512ull * UNROLL, A += 512ull * UNROLL, src += STEP * UNROLL) {
+        uint32_t w[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) w[u] = pgb_chunk_codes<GATHER>(row, src + STEP * u, sh);
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) pgb_emit_chunk<REPL>(A + 512ull * u, w[u], r8, l4, HINT);
+    }
+    for (; rowA < hi; rowA += 512, A += 512, src += STEP)
+        if (A < hi) pgb_emit_chunk<REPL>(A, pgb_chunk_codes<GATHER>(row, src, sh), r8, l4, HINT);
 }

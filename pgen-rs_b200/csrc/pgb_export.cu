@@ -569,15 +569,10 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
     auto out_before = [&](uint64_t i) { return (prefix_off[i] - prefix_off[0]) + i * fixed; };
     uint64_t seq = 0;
     uint64_t line = 0;
+    std::vector<uint64_t> shard_begin(G + 1), shard_byte(G + 1);
+    pgb_shard_plan(n_var, K, prefix_off, G, shard_begin.data(), shard_byte.data());
     for (int g = 0; g < G; g++) {
-        uint64_t end;
-        if (g == G - 1) end = n_var;
-        else {
-            const uint64_t target = total / G * (g + 1);
-            uint64_t lo = line, hi = n_var;
-            while (lo < hi) { uint64_t mid = (lo + hi) / 2; if (out_before(mid) < target) lo = mid + 1; else hi = mid; }
-            end = lo;
-        }
+        const uint64_t end = shard_begin[g + 1];
         work[g].seq_base = seq;
         while (line < end) {
             Chunk c;
@@ -655,6 +650,32 @@ bool is_pinned(const void *p) {
 }
 
 } // namespace
+
+extern "C" int pgb_shard_plan(uint64_t n_var, uint64_t n_kept_samples, const uint64_t *prefix_off, int n_shards,
+                              uint64_t *line_begin, uint64_t *byte_begin) {
+    if (n_shards <= 0 || !line_begin || (n_var && !prefix_off)) return PGB_E_ARG;
+    const uint64_t fixed = 4ull * n_kept_samples + 1ull;
+    auto out_before = [&](uint64_t i) { return i ? (prefix_off[i] - prefix_off[0]) + i * fixed : 0; };
+    const uint64_t total = out_before(n_var);
+    uint64_t line = 0;
+    line_begin[0] = 0;
+    if (byte_begin) byte_begin[0] = 0;
+    for (int g = 0; g < n_shards; g++) {
+        uint64_t end;
+        if (g == n_shards - 1) end = n_var;
+        else {
+            // first line boundary at or past g+1 equal shares of the output bytes
+            const uint64_t target = total / (uint64_t)n_shards * (uint64_t)(g + 1);
+            uint64_t lo = line, hi = n_var;
+            while (lo < hi) { uint64_t mid = (lo + hi) / 2; if (out_before(mid) < target) lo = mid + 1; else hi = mid; }
+            end = lo;
+        }
+        line_begin[g + 1] = end;
+        if (byte_begin) byte_begin[g + 1] = out_before(end);
+        line = end;
+    }
+    return PGB_OK;
+}
 
 extern "C" int pgb_open(const char *pgen_path, pgb_file **out) {
     pgb_clear_error();

@@ -185,30 +185,33 @@ __global__ void __launch_bounds__(K1_THREADS) k1_emit(const uint32_t *__restrict
 }
 
 // ------------------------------------------------------------------ K2 -----
+// Persistent CTAs (one resident wave) walk the (line, tile) items warp by warp with a grid
+// stride, so that the shared-memory tables are built once per CTA and neighbouring warps
+// write neighbouring lines at the same time.
 constexpr int K2_THREADS = 256;
 constexpr int K2_WARPS = K2_THREADS / 32;
 
-template <bool GATHER, int UNROLL, bool LUT>
+template <bool GATHER, int HINT, int REPL>
 __global__ void __launch_bounds__(K2_THREADS) k2_format_kernel(const pgb_k2_params p) {
-    __shared__ __align__(16) pgb_u4 s_lut[LUT ? 256 : 1];
-    if (LUT) {
-        s_lut[threadIdx.x] = pgb_lut_entry(threadIdx.x);
-        __syncthreads();
+    __shared__ __align__(16) pgb_u4 s_lut4[256 * REPL];
+    {
+        const pgb_u4 e = pgb_lut_entry(threadIdx.x);
+#pragma unroll
+        for (int g = 0; g < REPL; g++) s_lut4[threadIdx.x * REPL + g] = e;
     }
+    __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t n_items = p.n_lines * (uint64_t)p.n_tiles;
-    const uint64_t stride = (uint64_t)gridDim.x * K2_WARPS;
-    for (uint64_t item = (uint64_t)blockIdx.x * K2_WARPS + (threadIdx.x >> 5); item < n_items; item += stride) {
-        uint64_t line;
-        uint32_t tile;
-        if (p.n_tiles == 1) {
-            line = item;
-            tile = 0;
-        } else {
-            line = item / p.n_tiles;
-            tile = (uint32_t)(item - line * p.n_tiles);
+    const uint32_t first = blockIdx.x * K2_WARPS + (threadIdx.x >> 5); // < 2^31: the grid is one wave
+    uint64_t line = first / p.n_tiles;
+    uint32_t tile = first - (uint32_t)line * p.n_tiles;
+    while (line < p.n_lines) {
+        pgb_k2_item<GATHER, HINT, REPL>(p, line, tile, lane, s_lut4);
+        line += p.stride_lines;
+        tile += p.stride_tiles;
+        if (tile >= p.n_tiles) {
+            tile -= p.n_tiles;
+            line++;
         }
-        pgb_k2_item<GATHER, UNROLL, LUT>(p, line, tile, lane, s_lut);
     }
 }
 
@@ -300,19 +303,33 @@ extern "C" int pgb_dev_index_lines(const uint32_t *var_row, const uint64_t *pref
     return rc;
 }
 
-template <bool GATHER, int UNROLL, bool LUT>
-static int launch_k2(const pgb_k2_params &p, cudaStream_t st) {
+template <bool GATHER, int HINT, int REPL>
+static int launch_k2(pgb_k2_params &p, cudaStream_t st) {
     const uint64_t n_items = p.n_lines * (uint64_t)p.n_tiles;
     if (n_items == 0) return PGB_OK;
+    // one resident wave: SM count x CTAs per SM, cached per device
+    static int wave[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (wave[dev] == 0) {
+        int sms = 0, per_sm = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_format_kernel<GATHER, HINT, REPL>, K2_THREADS, 0) !=
+                cudaSuccess || per_sm <= 0)
+            per_sm = 4;
+        wave[dev] = sms * per_sm;
+    }
     uint64_t blocks = (n_items + K2_WARPS - 1) / K2_WARPS;
-    if (blocks > 0x40000000ull) blocks = 0x40000000ull;
-    k2_format_kernel<GATHER, UNROLL, LUT><<<(unsigned)blocks, K2_THREADS, 0, st>>>(p);
+    if (blocks > (uint64_t)wave[dev]) blocks = (uint64_t)wave[dev];
+    const uint64_t stride = blocks * K2_WARPS;
+    p.stride_lines = stride / p.n_tiles;
+    p.stride_tiles = (uint32_t)(stride - p.stride_lines * p.n_tiles);
+    k2_format_kernel<GATHER, HINT, REPL><<<(unsigned)blocks, K2_THREADS, 0, st>>>(p);
     return check_launch("k2_format_kernel");
 }
 
-// variant: bits 0-3 store hint (0 default, 1 .cs, 2 L1::no_allocate)
-//          bits 4-7 decode (0 ALU/PRMT, 1 shared-memory LUT)
-//          bits 8-11 unroll (0 => 4; 1, 2, 4)
+// variant: bits 0-3  store hint (0 => .cs streaming, the measured best; 1 => .cs; 2 => default write-back)
+//          bits 4-7  LUT copies (0 => 8 interleaved, bank-conflict-free; 1 => a single copy)
 //          bits 12-15 tile size = 4 KiB << n (0 => 16 KiB)
 extern "C" int pgb_dev_format_lines(const uint8_t *records, const pgb_line_meta *meta, uint64_t n_lines,
                                     const uint8_t *prefix_blob, const uint32_t *kidx, uint32_t n_kept,
@@ -327,30 +344,24 @@ extern "C" int pgb_dev_format_lines(const uint8_t *records, const pgb_line_meta 
     p.out = out;
     p.n_lines = n_lines;
     p.K = n_kept;
-    p.store_hint = variant & 0xF;
-    const int decode = (variant >> 4) & 0xF;
-    int unroll = (variant >> 8) & 0xF;
-    if (unroll == 0) unroll = 4;
+    const int hint = (variant & 0xF) == 2 ? 0 : 1;
+    const int single = (variant >> 4) & 0xF;
     const int tsel = (variant >> 12) & 0xF;
     p.tile_bytes = tsel ? (4096u << tsel) : 16384u;
     const uint64_t max_line = (uint64_t)max_prefix_len + 4ull * n_kept + 1ull;
     const uint64_t nt = (max_line + 511ull + p.tile_bytes - 1) / p.tile_bytes;
-    if (nt > 0xffffffffull) return PGB_E_ARG;
+    if (nt > 0x7fffffffull) return PGB_E_ARG;
     p.n_tiles = (uint32_t)nt;
+    p.stride_lines = 0;
+    p.stride_tiles = 0;
     cudaStream_t st = (cudaStream_t)stream;
-#define PGB_K2_CASE(G, U, L) return launch_k2<G, U, L>(p, st)
-    const bool g = kidx != nullptr, l = decode == 1;
-    if (unroll == 1) {
-        if (g) { if (l) PGB_K2_CASE(true, 1, true); else PGB_K2_CASE(true, 1, false); }
-        else   { if (l) PGB_K2_CASE(false, 1, true); else PGB_K2_CASE(false, 1, false); }
-    } else if (unroll == 2) {
-        if (g) { if (l) PGB_K2_CASE(true, 2, true); else PGB_K2_CASE(true, 2, false); }
-        else   { if (l) PGB_K2_CASE(false, 2, true); else PGB_K2_CASE(false, 2, false); }
-    } else {
-        if (g) { if (l) PGB_K2_CASE(true, 4, true); else PGB_K2_CASE(true, 4, false); }
-        else   { if (l) PGB_K2_CASE(false, 4, true); else PGB_K2_CASE(false, 4, false); }
+    const bool g = kidx != nullptr;
+    if (hint == 1) {
+        if (single) return g ? launch_k2<true, 1, 1>(p, st) : launch_k2<false, 1, 1>(p, st);
+        return g ? launch_k2<true, 1, 8>(p, st) : launch_k2<false, 1, 8>(p, st);
     }
-#undef PGB_K2_CASE
+    if (single) return g ? launch_k2<true, 0, 1>(p, st) : launch_k2<false, 0, 1>(p, st);
+    return g ? launch_k2<true, 0, 8>(p, st) : launch_k2<false, 0, 8>(p, st);
 }
 
 extern "C" int pgb_dev_synth_records(uint8_t *records, uint64_t pitch, uint64_t seed, uint64_t row0, uint64_t n_rows,

@@ -77,6 +77,7 @@ SYMBOLS = {
     "pgb_export_gt_vcf_mem": (_i, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _u64, C.POINTER(_u64), _vp, _i,
                                    C.POINTER(Stats)]),
     "pgb_body_bytes": (_u64, [_u64, _u64, _vp]),
+    "pgb_shard_plan": (_i, [_u64, _u64, _vp, _i, _vp, _vp]),
     "pgb_pfile_output_vcf": (_i, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _vp, _i, C.POINTER(Stats)]),
     "pgb_pfile_query": (_i, [C.c_char_p, C.c_char_p, C.c_char_p, _i, _i]),
     "pgb_plan_vcf": (_i, [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(_vp)]),
@@ -196,6 +197,16 @@ def export_to_bytes(f: PgenFile, var_idx, sam_idx, prefix_blob, prefix_off, devi
     out = np.empty(max(total, 1), dtype=np.uint8)
     n, _ = f.export_gt_vcf_mem(var_idx, sam_idx, prefix_blob, po, out.ctypes.data, total, devices)
     return out[:n].tobytes()
+
+
+def shard_plan(n_kept_samples: int, prefix_off, n_shards: int):
+    """pgb_shard_plan: (line_begin, byte_begin), each n_shards + 1 entries."""
+    po = np.ascontiguousarray(prefix_off, dtype=np.uint64)
+    lb = np.zeros(n_shards + 1, np.uint64)
+    bb = np.zeros(n_shards + 1, np.uint64)
+    _check(lib.pgb_shard_plan(len(po) - 1, n_kept_samples, po.ctypes.data, n_shards, lb.ctypes.data, bb.ctypes.data),
+           "pgb_shard_plan")
+    return lb, bb
 
 
 class VcfPlan:

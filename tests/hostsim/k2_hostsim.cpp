@@ -36,25 +36,31 @@ extern "C" int sim_format_lines(const uint8_t *records, uint64_t pitch, const ui
     p.out = out;
     p.n_lines = n_lines;
     p.K = K;
-    p.store_hint = variant & 0xF;
-    const int decode = (variant >> 4) & 0xF;
-    int unroll = (variant >> 8) & 0xF;
-    if (!unroll) unroll = 4;
+    const int hint = variant & 0xF;
+    const int single = (variant >> 4) & 0xF;
     const int tsel = (variant >> 12) & 0xF;
     p.tile_bytes = tsel ? (4096u << tsel) : 16384u;
     const uint64_t max_line = (uint64_t)maxp + 4ull * K + 1ull;
     p.n_tiles = (uint32_t)((max_line + 511ull + p.tile_bytes - 1) / p.tile_bytes);
-    pgb_u4 lut[256];
-    for (uint32_t b = 0; b < 256; b++) lut[b] = pgb_lut_entry(b);
+    p.stride_lines = 0;
+    p.stride_tiles = 0;
+    // the tables the kernel builds in shared memory
+    const int repl = single ? 1 : 8;
+    std::vector<pgb_u4> lut4(256 * repl);
+    for (uint32_t b = 0; b < 256; b++)
+        for (int g = 0; g < repl; g++) lut4[b * repl + g] = pgb_lut_entry(b);
+    const bool g = kidx != nullptr;
     for (uint64_t line = 0; line < n_lines; line++)
         for (uint32_t tile = 0; tile < p.n_tiles; tile++)
             for (uint32_t lane = 0; lane < 32; lane++) {
-                const bool g = kidx != nullptr, l = decode == 1;
-#define C(G, U, L) pgb_k2_item<G, U, L>(p, line, tile, lane, lut)
-                if (unroll == 1) { if (g) { if (l) C(true, 1, true); else C(true, 1, false); } else { if (l) C(false, 1, true); else C(false, 1, false); } }
-                else if (unroll == 2) { if (g) { if (l) C(true, 2, true); else C(true, 2, false); } else { if (l) C(false, 2, true); else C(false, 2, false); } }
-                else { if (g) { if (l) C(true, 4, true); else C(true, 4, false); } else { if (l) C(false, 4, true); else C(false, 4, false); } }
-#undef C
+                if (single) {
+                    if (g) pgb_k2_item<true, 0, 1>(p, line, tile, lane, lut4.data());
+                    else pgb_k2_item<false, 0, 1>(p, line, tile, lane, lut4.data());
+                } else {
+                    if (g) pgb_k2_item<true, 0, 8>(p, line, tile, lane, lut4.data());
+                    else pgb_k2_item<false, 0, 8>(p, line, tile, lane, lut4.data());
+                }
             }
+    (void)hint;
     return 0;
 }
