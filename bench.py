@@ -372,6 +372,16 @@ def run_b200(args, wl, rank, world, local_rank):
             traffic = None
 
     # ---- end to end through the C ABI with host buffers ----
+    if args.no_e2e:
+        if rank == 0:
+            print(json.dumps({"workload": args.workload, "value": value, "ms_per_step": dev_ms / args.steps, "k2_ms": k2_ms,
+                              "achieved_gbs": achieved, "frac": achieved / peak, "store_only_ceiling_gbs": fill_gbs,
+                              "variant": variant, "note": "kernel-only development line (--no-e2e); not a bench line"}), flush=True)
+        if sampler:
+            sampler.stop()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     image = torch.empty(12 + m * R, dtype=torch.uint8, pin_memory=True)
     image[:12] = torch.from_numpy(np.frombuffer(synth.pgen_header(m, n), dtype=np.uint8).copy())
     image[12:].copy_(recs[:m * R])
@@ -445,6 +455,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="chr22", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="kernel development: device-resident part only, short line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -204,6 +204,12 @@ int pgb_dev_synth_records(uint8_t *records, uint64_t pitch, uint64_t seed, uint6
 /* Store-only calibration kernel (16-byte streaming stores of a constant). */
 int pgb_dev_fill(uint8_t *dst, uint64_t bytes, int variant, void *stream);
 
+/* Store-only calibration with K2-like write patterns (tools/fill_sweep.py): segments of
+ * seg_rows x 512 bytes, `coop` (1/2/4/8) warps of a CTA per segment in bursts of `burst` rows,
+ * n_ctas persistent CTAs; seg_rows == 0 => grid-stride fill with `burst` strided stores per thread. */
+int pgb_dev_fill_pattern(uint8_t *dst, uint64_t bytes, uint32_t seg_rows, uint32_t coop, uint32_t burst,
+                         uint32_t n_ctas, int hint, void *stream);
+
 int pgb_device_count(void);
 const char *pgb_strerror(int status);
 /* Thread-local detail of the last failure on this thread (empty string if none). */

@@ -46,9 +46,7 @@ struct pgb_k2_params {
     uint32_t K;
     uint32_t n_tiles;    // tiles per line
     uint32_t tile_bytes; // multiple of 512
-    // grid-stride of the (line, tile) items, pre-divided on the host: stride = dl * n_tiles + dt
-    uint64_t stride_lines;
-    uint32_t stride_tiles;
+    uint32_t row_bytes_hint; // keep-all: bytes of a record worth prefetching (R + 1)
 };
 
 struct pgb_u4 {
@@ -183,9 +181,9 @@ PGB_DEV uint32_t pgb_chunk_codes(const uint8_t *row, const void *src, uint32_t s
 }
 
 template <bool GATHER, int HINT, int REPL>
-PGB_DEV void pgb_k2_item(const pgb_k2_params &p, uint64_t line, uint32_t tile, uint32_t lane, const pgb_u4 *lut4) {
+PGB_DEV void pgb_k2_item(const pgb_k2_params &p, const pgb_line_meta &m, uint32_t tile, uint32_t lane,
+                         const pgb_u4 *lut4) {
     constexpr int UNROLL = 4;
-    const pgb_line_meta m = pgb_ld_meta(p.meta + line);
     const uint32_t P = m.pfx_len;
     const uint64_t K4 = 4ull * p.K;
     const uint64_t a_ls = (uint64_t)(uintptr_t)p.out + m.line_off;
@@ -226,6 +224,70 @@ PGB_DEV void pgb_k2_item(const pgb_k2_params &p, uint64_t line, uint32_t tile, u
     constexpr uint32_t STEP = GATHER ? 128u * 4u : 32u;
     const int64_t q0 = (int64_t)(A - a_gs);   // may be negative only for a chunk that is skipped
     const uint8_t *src = GATHER ? (const uint8_t *)p.kidx + (q0 >> 2) * 4 : row + (q0 >> 4);
+    if (!GATHER) {
+        // Software-pipelined groups of UNROLL rows: the record bytes of group g+1 are requested
+        // before group g is formatted, so a line's DRAM/L2 latency is paid once, not once per
+        // group (round-1 ncu: 69 % of the stall samples were the first use of a loaded byte).
+        // mask bit u = this lane has a chunk in row u of the group; 0xF on the fast path.
+        const uint32_t lo_rel = (uint32_t)(lo - rowA), hi_rel = (uint32_t)(hi - rowA); // tile <= 128 MiB
+        uint32_t rel = lane * 16u;
+        uint32_t cb[2 * UNROLL], nb[2 * UNROLL];
+        uint32_t cm = 0, nm;
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const uint32_t ru = rel + 512u * u;
+            cb[2 * u] = cb[2 * u + 1] = 0;
+            if (ru >= lo_rel && ru < hi_rel) {
+                cm |= 1u << u;
+                cb[2 * u] = pgb_ld8(src + STEP * u);
+                cb[2 * u + 1] = pgb_ld8(src + STEP * u + 1);
+            }
+        }
+        for (;;) {
+            const uint32_t rel_n = rel + 512u * UNROLL;
+            const bool more = (rel_n & ~511u) < hi_rel; // warp-uniform
+            nm = 0;
+            if (more) {
+                if ((rel_n | 511u) + 512u * (UNROLL - 1) < hi_rel) { // every lane has all rows
+                    nm = (1u << UNROLL) - 1u;
+#pragma unroll
+                    for (int u = 0; u < UNROLL; u++) {
+                        nb[2 * u] = pgb_ld8(src + STEP * (UNROLL + u));
+                        nb[2 * u + 1] = pgb_ld8(src + STEP * (UNROLL + u) + 1);
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < UNROLL; u++) {
+                        nb[2 * u] = nb[2 * u + 1] = 0;
+                        if (rel_n + 512u * u < hi_rel) {
+                            nm |= 1u << u;
+                            nb[2 * u] = pgb_ld8(src + STEP * (UNROLL + u));
+                            nb[2 * u + 1] = pgb_ld8(src + STEP * (UNROLL + u) + 1);
+                        }
+                    }
+                }
+            }
+            if (cm == (1u << UNROLL) - 1u) {
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++)
+                    pgb_emit_chunk<REPL>(A + 512ull * u, pgb_prmt(cb[2 * u], cb[2 * u + 1], 0x1140u) >> sh, r8, l4, HINT);
+            } else {
+#pragma unroll
+                for (int u = 0; u < UNROLL; u++)
+                    if (cm & (1u << u))
+                        pgb_emit_chunk<REPL>(A + 512ull * u, pgb_prmt(cb[2 * u], cb[2 * u + 1], 0x1140u) >> sh, r8, l4,
+                                             HINT);
+            }
+            if (!more) break;
+#pragma unroll
+            for (int u = 0; u < 2 * UNROLL; u++) cb[u] = nb[u];
+            cm = nm;
+            rel = rel_n;
+            A += 512ull * UNROLL;
+            src += STEP * UNROLL;
+        }
+        return;
+    }
     if (rowA < lo) { // the first row starts in front of the body
         if (A >= lo && A < hi) pgb_emit_chunk<REPL>(A, pgb_chunk_codes<GATHER>(row, src, sh), r8, l4, HINT);
         rowA += 512; A += 512; src += STEP;

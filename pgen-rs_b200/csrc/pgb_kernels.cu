@@ -185,33 +185,92 @@ __global__ void __launch_bounds__(K1_THREADS) k1_emit(const uint32_t *__restrict
 }
 
 // ------------------------------------------------------------------ K2 -----
-// Persistent CTAs (one resident wave) walk the (line, tile) items warp by warp with a grid
-// stride, so that the shared-memory tables are built once per CTA and neighbouring warps
-// write neighbouring lines at the same time.
+// One CTA formats a batch of K2_ITEMS consecutive (line, tile) items, warp w taking items
+// w, w + 8, ...  The grid is NOT persistent: small CTAs handed out in order by the hardware
+// scheduler keep the set of lines being written compact and the warps staggered, which
+// measured 5-15 % more HBM write throughput than one resident wave walking the lines in
+// lockstep (tools/fill_sweep.py shows the same effect with pure stores).  Per CTA:
+//   1. threads 0..K2_ITEMS-1 fetch their item's pgb_line_meta into shared memory while the
+//      other threads build the text LUT;
+//   2. every item's record slice and prefix are requested into L2 (prefetch.global.L2), so the
+//      later items of each warp find their inputs on chip;
+//   3. the warps format their items (k2_core.cuh).
 constexpr int K2_THREADS = 256;
 constexpr int K2_WARPS = K2_THREADS / 32;
 
-template <bool GATHER, int HINT, int REPL>
+template <bool GATHER, int HINT, int REPL, int IPW>
 __global__ void __launch_bounds__(K2_THREADS) k2_format_kernel(const pgb_k2_params p) {
+    constexpr int ITEMS = K2_WARPS * IPW;
     __shared__ __align__(16) pgb_u4 s_lut4[256 * REPL];
+    __shared__ __align__(16) pgb_line_meta s_meta[ITEMS];
+    __shared__ uint32_t s_tile[ITEMS];
+    const uint64_t n_items = p.n_lines * (uint64_t)p.n_tiles;
+    const uint64_t item0 = (uint64_t)blockIdx.x * ITEMS;
+    if (threadIdx.x < ITEMS) {
+        const uint64_t item = item0 + threadIdx.x;
+        if (item < n_items) {
+            uint64_t line = item;
+            uint32_t tile = 0;
+            if (p.n_tiles > 1) {
+                line = item / p.n_tiles;
+                tile = (uint32_t)(item - line * p.n_tiles);
+            }
+            const uint4 *q = reinterpret_cast<const uint4 *>(p.meta + line);
+            uint4 *d = reinterpret_cast<uint4 *>(&s_meta[threadIdx.x]);
+            d[0] = __ldg(q);
+            d[1] = __ldg(q + 1);
+            s_tile[threadIdx.x] = tile;
+        }
+    }
     {
         const pgb_u4 e = pgb_lut_entry(threadIdx.x);
 #pragma unroll
         for (int g = 0; g < REPL; g++) s_lut4[threadIdx.x * REPL + g] = e;
     }
     __syncthreads();
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t first = blockIdx.x * K2_WARPS + (threadIdx.x >> 5); // < 2^31: the grid is one wave
-    uint64_t line = first / p.n_tiles;
-    uint32_t tile = first - (uint32_t)line * p.n_tiles;
-    while (line < p.n_lines) {
-        pgb_k2_item<GATHER, HINT, REPL>(p, line, tile, lane, s_lut4);
-        line += p.stride_lines;
-        tile += p.stride_tiles;
-        if (tile >= p.n_tiles) {
-            tile -= p.n_tiles;
-            line++;
+    { // L2 prefetch: 8 threads per item walk the 128-byte lines of its record slice and prefix
+        static_assert(ITEMS * 8 <= K2_THREADS || ITEMS * 8 % K2_THREADS == 0, "prefetch mapping");
+        for (uint32_t t = threadIdx.x; t < (uint32_t)ITEMS * 8u; t += K2_THREADS) {
+            const uint32_t slot = t >> 3, part = t & 7u;
+            if (item0 + slot >= n_items) continue;
+            const pgb_line_meta m = s_meta[slot];
+            const uint8_t *row = p.records + m.rec_off;
+            uint64_t j0 = 0, j1 = ((uint64_t)p.row_bytes_hint);
+            if (!GATHER && p.n_tiles > 1) {
+                // record bytes of this tile: GT offsets [t0 - a_gs, t1 - a_gs) / 16
+                const uint64_t a_ls = (uint64_t)(uintptr_t)p.out + m.line_off, a_gs = a_ls + m.pfx_len;
+                const uint64_t t0 = (a_ls & ~511ull) + (uint64_t)s_tile[slot] * p.tile_bytes, t1 = t0 + p.tile_bytes;
+                j0 = t0 > a_gs ? (t0 - a_gs) >> 4 : 0;
+                const uint64_t je = t1 > a_gs ? ((t1 - a_gs) >> 4) + 2 : 0;
+                j1 = je < j1 ? je : j1;
+            } else if (GATHER) {
+                if (p.n_tiles > 1 || p.K == 0) {
+                    j1 = 0; // the span of a tile's kept samples is not known here
+                } else {
+                    j0 = __ldg(p.kidx) >> 2;
+                    j1 = (__ldg(p.kidx + (p.K - 1)) >> 2) + 1;
+                }
+            }
+            if (j1 > j0) {
+                const uint64_t first = ((uint64_t)(uintptr_t)row + j0) & ~127ull;
+                const uint64_t last = (uint64_t)(uintptr_t)row + j1;
+                for (uint64_t a = first + 128ull * part; a < last && a < first + 128ull * 32; a += 128ull * 8)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+            }
+            if (part >= 6 && s_tile[slot] == 0 && m.pfx_len) {
+                const uint64_t pa = (uint64_t)(uintptr_t)(p.prefix_blob + m.pfx_off);
+                const uint64_t a = (pa & ~127ull) + 128ull * (part - 6);
+                if (a < pa + m.pfx_len) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+            }
         }
+    }
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#pragma unroll 1
+    for (int j = 0; j < IPW; j++) {
+        const uint32_t slot = j * K2_WARPS + warp;
+        if (item0 + slot >= n_items) break;
+        const pgb_line_meta m = s_meta[slot];
+        pgb_k2_item<GATHER, HINT, REPL>(p, m, s_tile[slot], lane, s_lut4);
     }
 }
 
@@ -254,6 +313,37 @@ __global__ void __launch_bounds__(256) fill_kernel(uint8_t *dst, uint64_t n16, i
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride)
         pgb_st16((uint64_t)(uintptr_t)dst + i * 16, 0x302F3009u, 0x312F3009u, 0x312F3109u, 0x2E2F2E09u, hint);
+}
+
+// Store-only calibration with K2-like write patterns: the output is cut into segments of
+// seg_rows x 512 bytes; `coop` warps of a CTA share a segment (row-interleaved in bursts of
+// `burst` rows); the (8 / coop) segment slots of all CTAs walk the segments with a grid stride.
+// Separates DRAM/L2 write behaviour from K2's compute.
+__global__ void __launch_bounds__(256) fill_segments_kernel(uint8_t *dst, uint64_t n_seg, uint32_t seg_rows, int hint,
+                                                            uint32_t coop, uint32_t burst) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t groups = 8u / coop;                 // segments in flight per CTA
+    const uint32_t sub = warp % coop;                  // this warp's share of the segment
+    const uint64_t seg_stride = (uint64_t)gridDim.x * groups;
+    for (uint64_t seg = (uint64_t)blockIdx.x * groups + warp / coop; seg < n_seg; seg += seg_stride) {
+        const uint64_t base = (uint64_t)(uintptr_t)dst + seg * seg_rows * 512ull + lane * 16u;
+        for (uint32_t r = sub * burst; r < seg_rows; r += burst * coop) {
+            for (uint32_t u = 0; u < burst; u++)
+                if (r + u < seg_rows)
+                    pgb_st16(base + (uint64_t)(r + u) * 512ull, 0x302F3009u, 0x312F3009u, 0x312F3109u, 0x2E2F2E09u, hint);
+        }
+    }
+}
+
+// Plain grid-stride fill whose every thread issues `burst` stores one grid stride apart per iteration.
+__global__ void __launch_bounds__(256) fill_strided_kernel(uint8_t *dst, uint64_t n16, int hint, uint32_t burst) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride * burst) {
+        for (uint32_t u = 0; u < burst; u++)
+            if (i + u * stride < n16)
+                pgb_st16((uint64_t)(uintptr_t)dst + (i + u * stride) * 16, 0x302F3009u, 0x312F3009u, 0x312F3109u,
+                         0x2E2F2E09u, hint);
+    }
 }
 
 // ---------------------------------------------------------- launchers ------
@@ -303,33 +393,34 @@ extern "C" int pgb_dev_index_lines(const uint32_t *var_row, const uint64_t *pref
     return rc;
 }
 
-template <bool GATHER, int HINT, int REPL>
-static int launch_k2(pgb_k2_params &p, cudaStream_t st) {
+template <bool GATHER, int HINT, int REPL, int IPW>
+static int launch_k2(const pgb_k2_params &p, cudaStream_t st) {
     const uint64_t n_items = p.n_lines * (uint64_t)p.n_tiles;
     if (n_items == 0) return PGB_OK;
-    // one resident wave: SM count x CTAs per SM, cached per device
-    static int wave[64] = {0};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
-    if (wave[dev] == 0) {
-        int sms = 0, per_sm = 0;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_format_kernel<GATHER, HINT, REPL>, K2_THREADS, 0) !=
-                cudaSuccess || per_sm <= 0)
-            per_sm = 4;
-        wave[dev] = sms * per_sm;
+    const uint64_t per_cta = (uint64_t)K2_WARPS * IPW;
+    const uint64_t blocks = (n_items + per_cta - 1) / per_cta;
+    if (blocks > 0x7fffffffull) {
+        pgb_set_error("K2 grid of %llu CTAs exceeds the launch limit", (unsigned long long)blocks);
+        return PGB_E_ARG;
     }
-    uint64_t blocks = (n_items + K2_WARPS - 1) / K2_WARPS;
-    if (blocks > (uint64_t)wave[dev]) blocks = (uint64_t)wave[dev];
-    const uint64_t stride = blocks * K2_WARPS;
-    p.stride_lines = stride / p.n_tiles;
-    p.stride_tiles = (uint32_t)(stride - p.stride_lines * p.n_tiles);
-    k2_format_kernel<GATHER, HINT, REPL><<<(unsigned)blocks, K2_THREADS, 0, st>>>(p);
+    k2_format_kernel<GATHER, HINT, REPL, IPW><<<(unsigned)blocks, K2_THREADS, 0, st>>>(p);
     return check_launch("k2_format_kernel");
 }
 
-// variant: bits 0-3  store hint (0 => .cs streaming, the measured best; 1 => .cs; 2 => default write-back)
-//          bits 4-7  LUT copies (0 => 8 interleaved, bank-conflict-free; 1 => a single copy)
+template <bool GATHER, int HINT, int REPL>
+static int launch_k2_ipw(const pgb_k2_params &p, cudaStream_t st, int ipw) {
+    if (ipw == 0) ipw = GATHER ? 4 : 2; // measured best on the chr22 shapes (profiles/README.md)
+    switch (ipw) {
+    case 1: return launch_k2<GATHER, HINT, REPL, 1>(p, st);
+    case 2: return launch_k2<GATHER, HINT, REPL, 2>(p, st);
+    case 8: return launch_k2<GATHER, HINT, REPL, 8>(p, st);
+    default: return launch_k2<GATHER, HINT, REPL, 4>(p, st);
+    }
+}
+
+// variant: bits 0-3  store hint (0 => .cs streaming, the measured best; 2 => default write-back)
+//          bits 4-7  LUT copies (0 => one copy; 1 => 8 interleaved bank-conflict-free copies)
+//          bits 8-11 items per warp (0 => 2 keep-all / 4 gather; 1, 2, 4, 8)
 //          bits 12-15 tile size = 4 KiB << n (0 => 16 KiB)
 extern "C" int pgb_dev_format_lines(const uint8_t *records, const pgb_line_meta *meta, uint64_t n_lines,
                                     const uint8_t *prefix_blob, const uint32_t *kidx, uint32_t n_kept,
@@ -345,23 +436,24 @@ extern "C" int pgb_dev_format_lines(const uint8_t *records, const pgb_line_meta 
     p.n_lines = n_lines;
     p.K = n_kept;
     const int hint = (variant & 0xF) == 2 ? 0 : 1;
-    const int single = (variant >> 4) & 0xF;
+    const int repl8 = (variant >> 4) & 0xF;
+    const int ipw = (variant >> 8) & 0xF;
     const int tsel = (variant >> 12) & 0xF;
     p.tile_bytes = tsel ? (4096u << tsel) : 16384u;
     const uint64_t max_line = (uint64_t)max_prefix_len + 4ull * n_kept + 1ull;
     const uint64_t nt = (max_line + 511ull + p.tile_bytes - 1) / p.tile_bytes;
     if (nt > 0x7fffffffull) return PGB_E_ARG;
     p.n_tiles = (uint32_t)nt;
-    p.stride_lines = 0;
-    p.stride_tiles = 0;
+    // bytes of a record worth prefetching: all of it for keep-all, up to the last kept sample otherwise
+    p.row_bytes_hint = kidx ? 0u : (n_kept + 3u) / 4u + 1u;
     cudaStream_t st = (cudaStream_t)stream;
     const bool g = kidx != nullptr;
     if (hint == 1) {
-        if (single) return g ? launch_k2<true, 1, 1>(p, st) : launch_k2<false, 1, 1>(p, st);
-        return g ? launch_k2<true, 1, 8>(p, st) : launch_k2<false, 1, 8>(p, st);
+        if (repl8) return g ? launch_k2_ipw<true, 1, 8>(p, st, ipw) : launch_k2_ipw<false, 1, 8>(p, st, ipw);
+        return g ? launch_k2_ipw<true, 1, 1>(p, st, ipw) : launch_k2_ipw<false, 1, 1>(p, st, ipw);
     }
-    if (single) return g ? launch_k2<true, 0, 1>(p, st) : launch_k2<false, 0, 1>(p, st);
-    return g ? launch_k2<true, 0, 8>(p, st) : launch_k2<false, 0, 8>(p, st);
+    if (repl8) return g ? launch_k2_ipw<true, 0, 8>(p, st, ipw) : launch_k2_ipw<false, 0, 8>(p, st, ipw);
+    return g ? launch_k2_ipw<true, 0, 1>(p, st, ipw) : launch_k2_ipw<false, 0, 1>(p, st, ipw);
 }
 
 extern "C" int pgb_dev_synth_records(uint8_t *records, uint64_t pitch, uint64_t seed, uint64_t row0, uint64_t n_rows,
@@ -377,6 +469,7 @@ extern "C" int pgb_dev_synth_records(uint8_t *records, uint64_t pitch, uint64_t 
     return check_launch("synth_records_kernel");
 }
 
+// variant: bits 0-3 store hint (0 default, 1 .cs streaming).
 extern "C" int pgb_dev_fill(uint8_t *dst, uint64_t bytes, int variant, void *stream) {
     if (!dst || ((uintptr_t)dst & 15)) return PGB_E_ARG;
     const uint64_t n16 = bytes / 16;
@@ -385,4 +478,18 @@ extern "C" int pgb_dev_fill(uint8_t *dst, uint64_t bytes, int variant, void *str
     if (blocks > 148ull * 32) blocks = 148ull * 32;
     fill_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(dst, n16, variant & 0xF);
     return check_launch("fill_kernel");
+}
+
+extern "C" int pgb_dev_fill_pattern(uint8_t *dst, uint64_t bytes, uint32_t seg_rows, uint32_t coop, uint32_t burst,
+                                    uint32_t n_ctas, int hint, void *stream) {
+    if (!dst || ((uintptr_t)dst & 15) || !n_ctas || !burst) return PGB_E_ARG;
+    if (coop != 1 && coop != 2 && coop != 4 && coop != 8) return PGB_E_ARG;
+    if (seg_rows == 0) {
+        fill_strided_kernel<<<n_ctas, 256, 0, (cudaStream_t)stream>>>(dst, bytes / 16, hint, burst);
+        return check_launch("fill_strided_kernel");
+    }
+    const uint64_t n_seg = bytes / (seg_rows * 512ull);
+    if (!n_seg) return PGB_OK;
+    fill_segments_kernel<<<n_ctas, 256, 0, (cudaStream_t)stream>>>(dst, n_seg, seg_rows, hint, coop, burst);
+    return check_launch("fill_segments_kernel");
 }

@@ -42,10 +42,9 @@ extern "C" int sim_format_lines(const uint8_t *records, uint64_t pitch, const ui
     p.tile_bytes = tsel ? (4096u << tsel) : 16384u;
     const uint64_t max_line = (uint64_t)maxp + 4ull * K + 1ull;
     p.n_tiles = (uint32_t)((max_line + 511ull + p.tile_bytes - 1) / p.tile_bytes);
-    p.stride_lines = 0;
-    p.stride_tiles = 0;
+    p.row_bytes_hint = 0;
     // the tables the kernel builds in shared memory
-    const int repl = single ? 1 : 8;
+    const int repl = single ? 8 : 1;
     std::vector<pgb_u4> lut4(256 * repl);
     for (uint32_t b = 0; b < 256; b++)
         for (int g = 0; g < repl; g++) lut4[b * repl + g] = pgb_lut_entry(b);
@@ -53,12 +52,12 @@ extern "C" int sim_format_lines(const uint8_t *records, uint64_t pitch, const ui
     for (uint64_t line = 0; line < n_lines; line++)
         for (uint32_t tile = 0; tile < p.n_tiles; tile++)
             for (uint32_t lane = 0; lane < 32; lane++) {
-                if (single) {
-                    if (g) pgb_k2_item<true, 0, 1>(p, line, tile, lane, lut4.data());
-                    else pgb_k2_item<false, 0, 1>(p, line, tile, lane, lut4.data());
+                if (!single) {
+                    if (g) pgb_k2_item<true, 0, 1>(p, meta[line], tile, lane, lut4.data());
+                    else pgb_k2_item<false, 0, 1>(p, meta[line], tile, lane, lut4.data());
                 } else {
-                    if (g) pgb_k2_item<true, 0, 8>(p, line, tile, lane, lut4.data());
-                    else pgb_k2_item<false, 0, 8>(p, line, tile, lane, lut4.data());
+                    if (g) pgb_k2_item<true, 0, 8>(p, meta[line], tile, lane, lut4.data());
+                    else pgb_k2_item<false, 0, 8>(p, meta[line], tile, lane, lut4.data());
                 }
             }
     (void)hint;
