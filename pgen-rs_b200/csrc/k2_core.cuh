@@ -202,12 +202,14 @@ PGB_DEV void pgb_k2_item(const pgb_k2_params &p, const pgb_line_meta &m, uint32_
         const uint64_t lo = a_ls > t0 ? a_ls : t0, hi = a_gs < t1 ? a_gs : t1;
         for (uint64_t a = lo + lane; a < hi; a += 32) pgb_st8(a, pgb_ld8(pfx + (a - a_ls)));
     }
-    { // GT bytes in front of the first aligned chunk
-        const uint64_t lo = a_gs > t0 ? a_gs : t0, hi = b0 < t1 ? b0 : t1;
-        for (uint64_t a = lo + lane; a < hi; a += 32) pgb_st8(a, pgb_gt_byte<GATHER>(p, row, K4, a - a_gs));
-    }
-    { // GT bytes behind the last aligned chunk, and the newline (pfile.rs:190)
-        const uint64_t lo = b1 > t0 ? b1 : t0, hi = a_le < t1 ? a_le : t1;
+    if (b0 < b1) {
+        // <= 15 GT bytes in front of the first aligned chunk (lanes 0-15) and <= 15 GT bytes + the
+        // newline (pfile.rs:190) behind the last one (lanes 16-31), in one pass
+        const uint64_t a = lane < 16 ? a_gs + lane : b1 + (lane - 16u);
+        const uint64_t end = lane < 16 ? b0 : a_le;
+        if (a < end && a >= t0 && a < t1) pgb_st8(a, pgb_gt_byte<GATHER>(p, row, K4, a - a_gs));
+    } else { // no aligned chunk inside the GT text: the whole GT region byte by byte
+        const uint64_t lo = a_gs > t0 ? a_gs : t0, hi = a_le < t1 ? a_le : t1;
         for (uint64_t a = lo + lane; a < hi; a += 32) pgb_st8(a, pgb_gt_byte<GATHER>(p, row, K4, a - a_gs));
     }
     const uint64_t lo = b0 > t0 ? b0 : t0, hi = b1 < t1 ? b1 : t1;
@@ -218,6 +220,23 @@ PGB_DEV void pgb_k2_item(const pgb_k2_params &p, const pgb_line_meta &m, uint32_
     const uint32_t sh = (delta >> 2) * 2u;                // 2-bit phase inside a record byte
     const pgb_u4 *l4 = lut4 + (lane & (uint32_t)(REPL - 1));
 
+    if (hi - lo <= 2048u) {
+        // Short body (short lines, e.g. a 10 % sample subset of 2 504): chunk-indexed instead of
+        // 512-byte-row-aligned, so that 62 chunks take two warp iterations, not three.
+        const uint32_t n_chunks = (uint32_t)(hi - lo) >> 4;
+        const uint32_t qlo = (uint32_t)(lo - a_gs);
+        for (uint32_t c = lane; c < n_chunks; c += 64) {
+            const uint32_t qa = qlo + 16u * c, qb = qa + 512u;
+            const bool two = c + 32 < n_chunks;
+            const void *sa = GATHER ? (const void *)(p.kidx + (qa >> 2)) : (const void *)(row + (qa >> 4));
+            const void *sb = GATHER ? (const void *)(p.kidx + (qb >> 2)) : (const void *)(row + (qb >> 4));
+            const uint32_t wa = pgb_chunk_codes<GATHER>(row, sa, sh);
+            const uint32_t wb = two ? pgb_chunk_codes<GATHER>(row, sb, sh) : 0u;
+            pgb_emit_chunk<REPL>(lo + 16ull * c, wa, r8, l4, HINT);
+            if (two) pgb_emit_chunk<REPL>(lo + 16ull * c + 512u, wb, r8, l4, HINT);
+        }
+        return;
+    }
     uint64_t rowA = lo & ~511ull;             // warp-uniform: start of the current 512-byte output row
     uint64_t A = rowA + (uint64_t)lane * 16u; // this lane's chunk in it
     // source of the chunk's codes; one output row further = 32 record bytes / 128 kept samples
