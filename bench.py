@@ -429,6 +429,54 @@ def run_b200(args, wl, rank, world, local_rank):
         torch.cuda.synchronize()
         for sl in (slice(0, 1 << 20), slice(max(0, total - (1 << 20)), total)):
             assert torch.equal(h_out[sl], d_out[sl].cpu()), "e2e and device-resident outputs differ"
+        # ---- end to end INCLUDING the file write (north_star's second e2e form): the same call
+        #      with an fd sink, as Pfile::output_vcf uses it.  Rank 0, N=1, 1 warm-up + 2 timed.
+        e2e_file = None
+        if rank == 0 and world == 1 and not args.no_file:
+            for where in (os.environ.get("PGB_BENCH_FILE_DIR"), "/dev/shm", tempfile.gettempdir()):
+                if not where or not os.path.isdir(where):
+                    continue
+                vfs = os.statvfs(where)
+                if vfs.f_bavail * vfs.f_frsize < total + (2 << 30):
+                    continue
+                path = os.path.join(where, "pgb_bench_%d.vcf" % os.getpid())
+                try:
+                    # storage calibration: plain pwrite() of the finished body from page-locked memory
+                    # into a fresh file on the same file system, one thread, no fsync
+                    mv = memoryview(h_out.numpy())[:min(total, 4 << 30)]
+                    fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+                    try:
+                        t0 = time.perf_counter()
+                        o = 0
+                        while o < len(mv):
+                            o += os.pwrite(fd, mv[o:o + (256 << 20)], o)
+                        pw_gbs = len(mv) / (time.perf_counter() - t0) / 1e9
+                    finally:
+                        os.close(fd)
+                    ts = []
+                    for it in range(3):
+                        fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+                        try:
+                            t0 = time.perf_counter()
+                            stf = f.export_gt_vcf(var, sam, blob_np, off_np, fd, devices=[local_rank])
+                            ts.append(time.perf_counter() - t0)
+                        finally:
+                            os.close(fd)
+                        assert os.path.getsize(path) == total
+                    with open(path, "rb") as fh:  # spot check against the in-memory result
+                        assert fh.read(1 << 20) == bytes(h_out[:1 << 20].numpy())
+                    tt = sum(ts[1:]) / 2
+                    e2e_file = {"value": genotypes_step / tt, "unit": UNIT, "vcf_gb_per_s": total / tt / 1e9,
+                                "ms_per_step": 1e3 * tt, "sink": "regular file in %s (%s), no fsync" % (
+                                    where, "tmpfs" if where == "/dev/shm" else "page cache"),
+                                "api": "pgb_export_gt_vcf (fd sink, parallel pwrite)", "chunks": int(stf.n_chunks),
+                                "roofline": {"bound": "storage", "achieved": total / tt / 1e9, "peak": pw_gbs, "unit": "GB/s",
+                                             "frac": total / tt / 1e9 / pw_gbs,
+                                             "peak_source": "single-thread pwrite of the same bytes to the same file system, measured in this run"}}
+                finally:
+                    if os.path.exists(path):
+                        os.unlink(path)
+                break
     clocks = sampler.stop() if sampler else None
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
@@ -455,7 +503,7 @@ def run_b200(args, wl, rank, world, local_rank):
                          "traffic": traffic, "kernel": "k2_format_kernel", "kernel_ms": k2_ms,
                          "algorithmic_bytes_per_launch": int(alg_bytes), "peak_source": peak_src,
                          "frac_of_nominal_8TBs": achieved / 8000.0, "store_only_ceiling_gbs": fill_gbs},
-            "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+            "e2e": e2e, "e2e_file": e2e_file, "cpu_baseline": cpu, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -470,6 +518,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="chr22", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-file", action="store_true", help="skip the e2e leg that writes a file")
     ap.add_argument("--no-e2e", action="store_true", help="kernel development: device-resident part only, short line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

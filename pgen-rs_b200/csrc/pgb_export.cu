@@ -25,6 +25,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -147,12 +148,15 @@ struct Chunk {
     uint32_t max_pfx;
 };
 
+class WritePool;
+
 struct Sink {
     int fd = -1;
     bool positional = false; // pwrite at absolute offsets
     uint64_t base = 0;
     uint8_t *mem = nullptr;
     bool mem_pinned = false;
+    WritePool *pool = nullptr; // positional sinks only
     // ordered (non-positional) writes
     std::mutex mu;
     std::condition_variable cv;
@@ -256,6 +260,83 @@ int write_fully(int fd, const uint8_t *src, uint64_t n, bool positional, uint64_
     return PGB_OK;
 }
 
+// Helper threads for positional sinks: a chunk that has landed in page-locked memory is cut
+// into pieces that are pwrite()n concurrently (one writer thread per device cannot keep a
+// tmpfs / page-cache sink busy: the copy into the page cache is CPU-bound).
+class WritePool {
+  public:
+    explicit WritePool(int n_threads) {
+        for (int i = 0; i < n_threads; i++) th_.emplace_back([this] { run(); });
+    }
+    ~WritePool() {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    // Writes [src, src+n) at file offset off, split into pieces; returns when all are done.
+    int write(int fd, const uint8_t *src, uint64_t n, uint64_t off) {
+        const uint64_t piece = std::max<uint64_t>(4ull << 20, align_up(n / (2 * (uint64_t)th_.size() + 1), 1 << 20));
+        Batch b;
+        for (uint64_t o = 0; o < n; o += piece) {
+            Task t{fd, src + o, std::min(piece, n - o), off + o, &b};
+            {
+                std::lock_guard<std::mutex> g(mu_);
+                b.pending++;
+                q_.push_back(t);
+            }
+            cv_.notify_one();
+        }
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return b.pending == 0; });
+        if (b.rc) pgb_set_error("%s", b.err);
+        return b.rc;
+    }
+
+  private:
+    struct Batch {
+        int pending = 0;
+        int rc = PGB_OK;
+        char err[160] = {0};
+    };
+    struct Task {
+        int fd;
+        const uint8_t *src;
+        uint64_t n, off;
+        Batch *batch;
+    };
+    void run() {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                t = q_.front();
+                q_.pop_front();
+            }
+            pgb_clear_error();
+            const int rc = write_fully(t.fd, t.src, t.n, true, t.off);
+            {
+                std::lock_guard<std::mutex> g(mu_);
+                if (rc && !t.batch->rc) {
+                    t.batch->rc = rc;
+                    snprintf(t.batch->err, sizeof t.batch->err, "%s", pgb_last_error());
+                }
+                t.batch->pending--;
+            }
+            done_cv_.notify_all();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    std::deque<Task> q_;
+    std::vector<std::thread> th_;
+    bool stop_ = false;
+};
+
 // Stage layout inside h_in/d_in:  [records | pad16 | prefix bytes | prefix_off u64[n+1] | var_row u32[n]]
 struct Stage {
     uint64_t rec_bytes, pfx_pos, pfx_bytes, off_pos, row_pos, total;
@@ -306,7 +387,8 @@ void writer_loop(Job *job, DeviceWork *w, std::deque<Pending> *q, std::mutex *qm
             if (sk->mem) {
                 if (!sk->mem_pinned) memcpy(sk->mem + ch.out_off, s.h_out, ch.out_bytes);
             } else if (sk->positional) {
-                rc = write_fully(sk->fd, s.h_out, ch.out_bytes, true, sk->base + ch.out_off);
+                rc = sk->pool ? sk->pool->write(sk->fd, s.h_out, ch.out_bytes, sk->base + ch.out_off)
+                              : write_fully(sk->fd, s.h_out, ch.out_bytes, true, sk->base + ch.out_off);
             } else {
                 const uint64_t seq = w->seq_base + p.chunk;
                 std::unique_lock<std::mutex> lk(sk->mu);
@@ -612,6 +694,19 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
     job.prefix_blob = prefix_blob; job.prefix_off = prefix_off; job.sink = sink;
     job.variant = (int)env_u64("PGB_K2_VARIANT", 0);
 
+    std::unique_ptr<WritePool> pool;
+    if (sink->fd >= 0 && sink->positional) {
+        // regular file: size it once so that concurrent pwrite()s do not serialise on extending it
+        struct stat st;
+        if (fstat(sink->fd, &st) == 0 && S_ISREG(st.st_mode) && (uint64_t)st.st_size < sink->base + total)
+            (void)!ftruncate(sink->fd, (off_t)(sink->base + total));
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const int n_writers = (int)env_u64("PGB_WRITERS", std::min<uint64_t>(8, std::max(1u, hw / 2)));
+        if (n_writers > 1) {
+            pool.reset(new WritePool(n_writers));
+            sink->pool = pool.get();
+        }
+    }
     if (G == 1) run_device(&job, &work[0]);
     else {
         std::vector<std::thread> th;
