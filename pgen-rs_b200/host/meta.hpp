@@ -37,23 +37,38 @@ class MetaTable {
     void parse();
     const std::vector<std::string> &headers() const { return headers_; }
     size_t n_cols() const { return headers_.size(); }
-    size_t n_rows() const { return n_rows_; }
+    size_t n_rows() const { return rows_.size(); }
     std::string_view field(size_t row, size_t col) const {
-        const Span &s = fields_[row * headers_.size() + col];
-        return std::string_view(data_.data() + s.off, s.len);
+        const RowSpan &r = rows_[row];
+        const uint32_t *fs = &fstart_[row * headers_.size()];
+        const uint32_t b = fs[col];
+        const uint32_t e = col + 1 < headers_.size() ? fs[col + 1] - 1 : r.len;
+        return std::string_view(data_.data() + r.off + b, e - b);
     }
+    // The record's text without its terminator: the fields joined by '\t', exactly as in the file.
+    std::string_view row_text(size_t row) const { return std::string_view(data_.data() + rows_[row].off, rows_[row].len); }
     void row(size_t r, std::vector<std::string_view> *out) const;
 
+    // Worker threads used for parsing / filtering large tables (1 for small inputs).
+    static unsigned worker_threads(size_t bytes);
+
   private:
-    struct Span {
-        uint64_t off;
-        uint32_t len;
+    struct RowSpan {
+        uint64_t off; // first byte of the record in data_
+        uint32_t len; // bytes up to (not including) the terminator
     };
+    struct Block { // parse result of one line-aligned slice of the file
+        std::vector<RowSpan> rows;
+        std::vector<uint32_t> fstart;
+        std::string error;
+    };
+    void parse_block(size_t begin, size_t end, size_t n_cols, size_t first_record_no, Block *out) const;
+
     std::string path_;
     std::string data_;
     std::vector<std::string> headers_;
-    std::vector<Span> fields_;
-    size_t n_rows_ = 0;
+    std::vector<RowSpan> rows_;     // data records (header excluded)
+    std::vector<uint32_t> fstart_;  // n_rows x n_cols field starts relative to the record
     bool parsed_ = false;
 };
 

@@ -7,6 +7,7 @@
 #include <unistd.h>
 
 #include <memory>
+#include <thread>
 
 #include "expr.hpp"
 
@@ -71,13 +72,38 @@ std::vector<uint32_t> filter_metadata(MetaTable &table, const std::optional<std:
         }
         // The reference re-parses the expression for every row (pfile.rs:328), so a bad
         // expression only surfaces when there is at least one row.
-        std::unique_ptr<Expr> ex;
-        std::vector<std::string_view> row;
-        for (size_t i = 0; i < n; i++) {
-            if (!ex) ex = std::make_unique<Expr>(*query, table.headers());
-            table.row(i, &row);
-            if (ex->eval_boolean(row)) kept.push_back((uint32_t)i);
+        if (n == 0) return kept;
+        const unsigned T = n < 65536 ? 1u : MetaTable::worker_threads(table.data().size());
+        std::vector<std::vector<uint32_t>> part(T);
+        std::vector<std::string> err(T);
+        std::vector<size_t> err_row(T, SIZE_MAX);
+        auto work = [&](unsigned t) {
+            const size_t a = n / T * t, b = t + 1 == T ? n : n / T * (t + 1);
+            size_t i = a;
+            try {
+                Expr ex(*query, table.headers()); // one parsed expression per worker
+                std::vector<std::string_view> row;
+                for (; i < b; i++) {
+                    table.row(i, &row);
+                    if (ex.eval_boolean(row)) part[t].push_back((uint32_t)i);
+                }
+            } catch (const ExprError &e) {
+                err[t] = e.msg;
+                err_row[t] = i;
+            }
+        };
+        if (T == 1) work(0);
+        else {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < T; t++) th.emplace_back(work, t);
+            for (auto &x : th) x.join();
         }
+        for (unsigned t = 0; t < T; t++) // the first failing row in file order is the one the reference panics on
+            if (err_row[t] != SIZE_MAX) throw ExprError{err[t]};
+        size_t total = 0;
+        for (auto &v : part) total += v.size();
+        kept.reserve(total);
+        for (auto &v : part) kept.insert(kept.end(), v.begin(), v.end());
     } catch (const MetaError &e) {
         throw PfileError{e.status, e.msg};
     } catch (const ExprError &e) {
@@ -148,27 +174,36 @@ VcfPlan Pfile::plan_vcf(const std::optional<std::string> &sam_query, const std::
         }
         h.push_back('\n');
 
-        // line prefixes, pfile.rs:157-161: every field + '\t', then "GT"
-        const size_t nv = plan.var_idx.size(), nc = pvar.n_cols();
+        // line prefixes, pfile.rs:157-161: every field + '\t', then "GT".  Without csv quoting a
+        // record's fields joined by '\t' are its text in the file, so one copy per kept row.
+        const size_t nv = plan.var_idx.size();
         plan.prefix_off.resize(nv + 1);
         uint64_t total = 0;
         for (size_t k = 0; k < nv; k++) {
             plan.prefix_off[k] = total;
-            for (size_t c = 0; c < nc; c++) total += pvar.field(plan.var_idx[k], c).size() + 1;
-            total += 2;
+            total += pvar.row_text(plan.var_idx[k]).size() + 3;
         }
         plan.prefix_off[nv] = total;
         plan.prefix_blob.resize(total);
-        uint8_t *w = plan.prefix_blob.data();
-        for (size_t k = 0; k < nv; k++) {
-            for (size_t c = 0; c < nc; c++) {
-                std::string_view f = pvar.field(plan.var_idx[k], c);
-                memcpy(w, f.data(), f.size());
-                w += f.size();
-                *w++ = '\t';
+        uint8_t *base = plan.prefix_blob.data();
+        const unsigned T = total < (8u << 20) ? 1u : MetaTable::worker_threads(total);
+        auto fill = [&](unsigned t) {
+            const size_t a = nv / T * t, b = t + 1 == T ? nv : nv / T * (t + 1);
+            for (size_t k = a; k < b; k++) {
+                const std::string_view r = pvar.row_text(plan.var_idx[k]);
+                uint8_t *w = base + plan.prefix_off[k];
+                memcpy(w, r.data(), r.size());
+                w += r.size();
+                w[0] = '\t';
+                w[1] = 'G';
+                w[2] = 'T';
             }
-            *w++ = 'G';
-            *w++ = 'T';
+        };
+        if (T == 1) fill(0);
+        else {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < T; t++) th.emplace_back(fill, t);
+            for (auto &x : th) x.join();
         }
     } catch (const MetaError &e) {
         throw PfileError{e.status, e.msg};
