@@ -117,6 +117,10 @@ int pgb_export_gt_vcf_mem(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, 
 int pgb_shard_plan(uint64_t n_var, uint64_t n_kept_samples, const uint64_t *prefix_off, int n_shards,
                    uint64_t *line_begin, uint64_t *byte_begin);
 
+/* The per-device staging buffers, streams and events the export functions use are cached
+ * process-wide across calls and handles; this frees the ones no export is using. */
+void pgb_release_buffers(void);
+
 /* Body size in bytes for the given selection: sum(P_i) + n_var * (4K + 1). */
 uint64_t pgb_body_bytes(uint64_t n_var, uint64_t n_kept_samples, const uint64_t *prefix_off);
 

@@ -91,7 +91,6 @@ struct pgb_file {
     uint64_t bytes = 0; // file or image size
     uint32_t M = 0, N = 0, R = 0;
     std::mutex mu; // one export at a time per handle
-    std::vector<DeviceCtx *> ctx;
 };
 
 namespace {
@@ -137,6 +136,56 @@ void free_ctx(DeviceCtx *c) {
     }
     delete c;
 }
+
+// Per-device buffers (page-locked staging, device slots, streams, events) are process-wide
+// and outlive the pgb_file handles: a CLI-style host that opens, exports and closes per call
+// would otherwise pay ~30 ms of cudaHostAlloc/cudaMalloc on every export.  An export owns the
+// contexts of its devices for its duration (in_use), so concurrent exports on one device
+// queue up.  pgb_release_buffers() frees everything that is idle.
+struct CtxRegistry {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<DeviceCtx *> all;
+    std::vector<bool> in_use;
+} g_registry;
+
+// Acquires (creating on first use) the contexts of `devs` in ascending device order.
+void acquire_ctxs(const std::vector<int> &devs, std::vector<DeviceCtx *> *out) {
+    std::vector<int> order(devs);
+    std::sort(order.begin(), order.end());
+    std::unique_lock<std::mutex> lk(g_registry.mu);
+    out->assign(devs.size(), nullptr);
+    for (int d : order) {
+        size_t idx = g_registry.all.size();
+        for (size_t i = 0; i < g_registry.all.size(); i++)
+            if (g_registry.all[i]->device == d) idx = i;
+        if (idx == g_registry.all.size()) {
+            DeviceCtx *c = new DeviceCtx();
+            c->device = d;
+            g_registry.all.push_back(c);
+            g_registry.in_use.push_back(false);
+        }
+        g_registry.cv.wait(lk, [&] { return !g_registry.in_use[idx]; });
+        g_registry.in_use[idx] = true;
+        for (size_t g = 0; g < devs.size(); g++)
+            if (devs[g] == d) (*out)[g] = g_registry.all[idx];
+    }
+}
+
+void release_ctxs(const std::vector<DeviceCtx *> &ctxs) {
+    {
+        std::lock_guard<std::mutex> lk(g_registry.mu);
+        for (DeviceCtx *c : ctxs)
+            for (size_t i = 0; i < g_registry.all.size(); i++)
+                if (g_registry.all[i] == c) g_registry.in_use[i] = false;
+    }
+    g_registry.cv.notify_all();
+}
+
+struct CtxLease {
+    std::vector<DeviceCtx *> ctxs;
+    ~CtxLease() { release_ctxs(ctxs); }
+};
 
 struct Chunk {
     uint64_t a, b;       // line range [a, b)
@@ -276,7 +325,8 @@ class WritePool {
         cv_.notify_all();
         for (auto &t : th_) t.join();
     }
-    // Writes [src, src+n) at file offset off, split into pieces; returns when all are done.
+    // Writes [src, src+n) at file offset off (fd >= 0) or copies it to memory address off (fd < 0),
+    // split into pieces; returns when all are done.
     int write(int fd, const uint8_t *src, uint64_t n, uint64_t off) {
         const uint64_t piece = std::max<uint64_t>(4ull << 20, align_up(n / (2 * (uint64_t)th_.size() + 1), 1 << 20));
         Batch b;
@@ -318,7 +368,9 @@ class WritePool {
                 q_.pop_front();
             }
             pgb_clear_error();
-            const int rc = write_fully(t.fd, t.src, t.n, true, t.off);
+            int rc = PGB_OK;
+            if (t.fd < 0) memcpy((void *)(uintptr_t)t.off, t.src, t.n);
+            else rc = write_fully(t.fd, t.src, t.n, true, t.off);
             {
                 std::lock_guard<std::mutex> g(mu_);
                 if (rc && !t.batch->rc) {
@@ -385,7 +437,10 @@ void writer_loop(Job *job, DeviceWork *w, std::deque<Pending> *q, std::mutex *qm
             Sink *sk = job->sink;
             int rc = PGB_OK;
             if (sk->mem) {
-                if (!sk->mem_pinned) memcpy(sk->mem + ch.out_off, s.h_out, ch.out_bytes);
+                if (!sk->mem_pinned) {
+                    if (sk->pool) rc = sk->pool->write(-1, s.h_out, ch.out_bytes, (uint64_t)(uintptr_t)(sk->mem + ch.out_off));
+                    else memcpy(sk->mem + ch.out_off, s.h_out, ch.out_bytes);
+                }
             } else if (sk->positional) {
                 rc = sk->pool ? sk->pool->write(sk->fd, s.h_out, ch.out_bytes, sk->base + ch.out_off)
                               : write_fully(sk->fd, s.h_out, ch.out_bytes, true, sk->base + ch.out_off);
@@ -631,19 +686,14 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
         if (d < 0 || d >= n_avail) { pgb_set_error("device %d not present (%d visible)", d, n_avail); return PGB_E_NO_DEVICE; }
     const int G = (int)devs.size();
 
+    for (int g = 0; g < G; g++)
+        for (int h = 0; h < g; h++)
+            if (devs[h] == devs[g]) { pgb_set_error("duplicate device id"); return PGB_E_ARG; }
     std::lock_guard<std::mutex> file_lock(f->mu);
     std::vector<DeviceWork> work(G);
-    for (int g = 0; g < G; g++) {
-        DeviceCtx *c = nullptr;
-        for (DeviceCtx *x : f->ctx) if (x->device == devs[g]) c = x;
-        for (int h = 0; h < g; h++) if (devs[h] == devs[g]) { pgb_set_error("duplicate device id"); return PGB_E_ARG; }
-        if (!c) {
-            c = new DeviceCtx();
-            c->device = devs[g];
-            f->ctx.push_back(c);
-        }
-        work[g].ctx = c;
-    }
+    CtxLease lease;
+    acquire_ctxs(devs, &lease.ctxs);
+    for (int g = 0; g < G; g++) work[g].ctx = lease.ctxs[g];
 
     // ---- plan: contiguous line ranges per device balanced by output bytes, then chunks ----
     const uint64_t chunk_out = env_u64("PGB_CHUNK_MB", 256) << 20;
@@ -695,11 +745,13 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
     job.variant = (int)env_u64("PGB_K2_VARIANT", 0);
 
     std::unique_ptr<WritePool> pool;
-    if (sink->fd >= 0 && sink->positional) {
-        // regular file: size it once so that concurrent pwrite()s do not serialise on extending it
-        struct stat st;
-        if (fstat(sink->fd, &st) == 0 && S_ISREG(st.st_mode) && (uint64_t)st.st_size < sink->base + total)
-            (void)!ftruncate(sink->fd, (off_t)(sink->base + total));
+    if ((sink->fd >= 0 && sink->positional) || (sink->mem && !sink->mem_pinned && total > (64u << 20))) {
+        if (sink->fd >= 0) {
+            // regular file: size it once so that concurrent pwrite()s do not serialise on extending it
+            struct stat st;
+            if (fstat(sink->fd, &st) == 0 && S_ISREG(st.st_mode) && (uint64_t)st.st_size < sink->base + total)
+                (void)!ftruncate(sink->fd, (off_t)(sink->base + total));
+        }
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
         const int n_writers = (int)env_u64("PGB_WRITERS", std::min<uint64_t>(8, std::max(1u, hw / 2)));
         if (n_writers > 1) {
@@ -820,9 +872,23 @@ extern "C" void pgb_dims(const pgb_file *f, uint32_t *n_variants, uint32_t *n_sa
 
 extern "C" void pgb_close(pgb_file *f) {
     if (!f) return;
-    for (DeviceCtx *c : f->ctx) free_ctx(c);
     if (f->fd >= 0) close(f->fd);
     delete f;
+}
+
+extern "C" void pgb_release_buffers(void) {
+    std::vector<DeviceCtx *> idle;
+    {
+        std::lock_guard<std::mutex> lk(g_registry.mu);
+        for (size_t i = 0; i < g_registry.all.size();) {
+            if (!g_registry.in_use[i]) {
+                idle.push_back(g_registry.all[i]);
+                g_registry.all.erase(g_registry.all.begin() + (long)i);
+                g_registry.in_use.erase(g_registry.in_use.begin() + (long)i);
+            } else i++;
+        }
+    }
+    for (DeviceCtx *c : idle) free_ctx(c);
 }
 
 extern "C" int pgb_export_gt_vcf(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint32_t *sam_idx,

@@ -76,6 +76,7 @@ SYMBOLS = {
     "pgb_export_gt_vcf": (_i, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _i, _vp, _i, C.POINTER(Stats)]),
     "pgb_export_gt_vcf_mem": (_i, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _u64, C.POINTER(_u64), _vp, _i,
                                    C.POINTER(Stats)]),
+    "pgb_release_buffers": (None, []),
     "pgb_body_bytes": (_u64, [_u64, _u64, _vp]),
     "pgb_shard_plan": (_i, [_u64, _u64, _vp, _i, _vp, _vp]),
     "pgb_pfile_output_vcf": (_i, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _vp, _i, C.POINTER(Stats)]),

@@ -106,15 +106,18 @@ def cfg5_full():
     fd = os.open("/dev/null", os.O_WRONLY)
     try:
         with pgb200.PgenFile(image_ptr=image.data_ptr(), image_bytes=image.numel()) as f:
-            t0 = time.perf_counter()
-            s = f.export_gt_vcf(None, None, blob, off, fd, devices=[0])
-            dt = time.perf_counter() - t0
+            dts = []
+            for _ in range(2):  # the second pass finds every buffer allocated
+                t0 = time.perf_counter()
+                s = f.export_gt_vcf(None, None, blob, off, fd, devices=[0])
+                dts.append(time.perf_counter() - t0)
+            dt = dts[1]
     finally:
         os.close(fd)
     return {"config": "5-full", "genotypes": int(s.genotypes), "vcf_bytes": int(s.bytes_out), "wall_s": dt,
             "genotypes_per_s": s.genotypes / dt, "vcf_gb_per_s": s.bytes_out / dt / 1e9, "device_ms_sum": s.device_ms,
             "device_genotypes_per_s": s.genotypes / (s.device_ms * 1e-3), "chunks": int(s.n_chunks),
-            "sink": "/dev/null (ordered writes), output ring-buffered through 3 page-locked slots"}
+            "first_pass_wall_s": dts[0], "sink": "/dev/null (ordered writes), output ring-buffered through 3 page-locked slots"}
 
 
 def main():
