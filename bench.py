@@ -389,10 +389,11 @@ def run_b200(args, wl, rank, world, local_rank):
     torch.cuda.synchronize()
     h_out = torch.empty(total + 64, dtype=torch.uint8, pin_memory=True)
     # PCIe calibration: plain device->host copies of 1 GiB into the same page-locked buffer
+    # (all ranks at the same time: on a multi-GPU box the host side is shared)
     cal = min(total, 1 << 30)
     ca, cb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     h_out[:cal].copy_(d_out[:cal], non_blocking=True)
-    torch.cuda.synchronize()
+    barrier()
     ca.record()
     for _ in range(3):
         h_out[:cal].copy_(d_out[:cal], non_blocking=True)
@@ -422,7 +423,7 @@ def run_b200(args, wl, rank, world, local_rank):
                "launches_per_step": int(e_launch // args.steps), "chunks_per_step": int(st.n_chunks),
                "roofline": {"bound": "pcie_d2h", "achieved": total * args.steps / e2e_s / 1e9, "peak": d2h_gbs,
                             "unit": "GB/s per GPU", "frac": total * args.steps / e2e_s / 1e9 / d2h_gbs,
-                            "peak_source": "cudaMemcpyAsync device->pinned host, 1 GiB x3, measured in this run"}}
+                            "peak_source": "cudaMemcpyAsync device->pinned host, 1 GiB x3, all ranks concurrently, measured in this run"}}
         # parity spot check of the e2e result against the device-resident one (first/last 1 MiB)
         torch.cuda.synchronize()
         k1(); k2()

@@ -17,6 +17,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -206,6 +207,7 @@ struct Sink {
     uint8_t *mem = nullptr;
     bool mem_pinned = false;
     WritePool *pool = nullptr; // positional sinks only
+    uint8_t *map = nullptr;    // regular-file sink mapped MAP_SHARED: map[0] is file offset `base`
     // ordered (non-positional) writes
     std::mutex mu;
     std::condition_variable cv;
@@ -222,6 +224,13 @@ struct Job {
     const uint64_t *prefix_off;
     Sink *sink;
     int variant;
+    bool trace = false;
+    std::chrono::steady_clock::time_point t0;
+    void lap(const char *what, size_t ci) const {
+        if (trace)
+            fprintf(stderr, "[pgb]   chunk %zu %-10s +%.3f ms\n", ci, what,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
     std::atomic<int> status{PGB_OK};
     std::mutex err_mu;
     char err[512] = {0};
@@ -432,6 +441,7 @@ void writer_loop(Job *job, DeviceWork *w, std::deque<Pending> *q, std::mutex *qm
             pgb_set_error("cudaEventSynchronize: %s", cudaGetErrorString(e));
             job->fail(PGB_E_CUDA);
         } else if (job->status.load() == PGB_OK) {
+            job->lap("d2h done", p.chunk);
             float ms = 0;
             if (cudaEventElapsedTime(&ms, s.ev_k0, s.ev_k1) == cudaSuccess) w->device_ms += ms;
             Sink *sk = job->sink;
@@ -441,6 +451,11 @@ void writer_loop(Job *job, DeviceWork *w, std::deque<Pending> *q, std::mutex *qm
                     if (sk->pool) rc = sk->pool->write(-1, s.h_out, ch.out_bytes, (uint64_t)(uintptr_t)(sk->mem + ch.out_off));
                     else memcpy(sk->mem + ch.out_off, s.h_out, ch.out_bytes);
                 }
+            } else if (sk->map) {
+                // page-cache pages are filled by parallel copies through the mapping: buffered pwrite()s
+                // to one inode serialise on its lock (measured: 4-5 GB/s however many threads)
+                if (sk->pool) rc = sk->pool->write(-1, s.h_out, ch.out_bytes, (uint64_t)(uintptr_t)(sk->map + ch.out_off));
+                else memcpy(sk->map + ch.out_off, s.h_out, ch.out_bytes);
             } else if (sk->positional) {
                 rc = sk->pool ? sk->pool->write(sk->fd, s.h_out, ch.out_bytes, sk->base + ch.out_off)
                               : write_fully(sk->fd, s.h_out, ch.out_bytes, true, sk->base + ch.out_off);
@@ -527,6 +542,7 @@ int run_device_inner(Job *job, DeviceWork *w, std::deque<Pending> &q, std::mutex
             c->cv.wait(lk, [&] { return !s.busy; });
             s.busy = true;
         }
+        job->lap("slot free", ci);
         const bool rec_direct = f->image && f->image_pinned && ch.dense; // DMA records straight from the image
         const Stage lay = stage_layout(*job, ch, !rec_direct);
         const uint64_t n = ch.b - ch.a;
@@ -559,6 +575,7 @@ int run_device_inner(Job *job, DeviceWork *w, std::deque<Pending> &q, std::mutex
             else for (uint64_t i = 0; i < n; i++) vr[i] = (uint32_t)i;
         }
 
+        job->lap("staged", ci);
         // -- H2D, K1, K2, D2H on the slot's stream
         cudaStream_t st = s.stream;
         uint8_t *d_stage = s.d_in + d_rec_region;
@@ -587,6 +604,7 @@ int run_device_inner(Job *job, DeviceWork *w, std::deque<Pending> &q, std::mutex
         CU(cudaMemcpyAsync(dst, s.d_out, ch.out_bytes, cudaMemcpyDeviceToHost, st));
         w->d2h += ch.out_bytes;
         CU(cudaEventRecord(s.ev_done, st));
+        job->lap("enqueued", ci);
         {
             std::lock_guard<std::mutex> lk(qmu);
             q.push_back(Pending{si, ci});
@@ -627,6 +645,12 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
                 const uint8_t *prefix_blob, const uint64_t *prefix_off, Sink *sink, uint64_t out_cap, uint64_t *out_len,
                 const int *device_ids, int n_devices, pgb_stats *stats) {
     const auto t_begin = std::chrono::steady_clock::now();
+    const bool trace = env_u64("PGB_TRACE", 0) != 0;
+    auto lap = [&](const char *what) {
+        if (trace)
+            fprintf(stderr, "[pgb] %-12s +%.3f ms\n", what,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
     pgb_clear_error();
     if (stats) memset(stats, 0, sizeof *stats);
     if (!f) return PGB_E_ARG;
@@ -672,6 +696,7 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
     }
     if (n_var == 0) return PGB_OK;
 
+    lap("validated");
     // ---- devices ----
     int n_avail = 0;
     if (cudaGetDeviceCount(&n_avail) != cudaSuccess || n_avail <= 0) {
@@ -695,6 +720,7 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
     acquire_ctxs(devs, &lease.ctxs);
     for (int g = 0; g < G; g++) work[g].ctx = lease.ctxs[g];
 
+    lap("ctx leased");
     // ---- plan: contiguous line ranges per device balanced by output bytes, then chunks ----
     const uint64_t chunk_out = env_u64("PGB_CHUNK_MB", 256) << 20;
     const uint64_t chunk_in = env_u64("PGB_CHUNK_IN_MB", 128) << 20;
@@ -718,8 +744,8 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
                 if (ob > chunk_out) break;
                 const uint64_t v = var_idx ? var_idx[b] : b;
                 const uint64_t nmin = std::min(vmin, v), nmax = std::max(vmax, v);
-                const uint64_t cover = (nmax - nmin + 1) * R, compact = (b + 1 - line) * (uint64_t)R;
-                if (std::min(cover, compact) > chunk_in) break;
+                const uint64_t compact = (b + 1 - line) * (uint64_t)R; // bytes of the kept rows alone
+                if (compact > chunk_in) break;
                 if ((nmax - nmin) >= 0xffffffffull) break;
                 vmin = nmin; vmax = nmax;
                 maxp = std::max(maxp, (uint32_t)(prefix_off[b + 1] - prefix_off[b]));
@@ -728,7 +754,9 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
             c.b = b;
             c.v0 = vmin; c.v1 = vmax;
             const uint64_t cover_rows = vmax - vmin + 1, kept_rows = b - line;
-            c.dense = cover_rows <= 4 * kept_rows && cover_rows * R <= chunk_in + R;
+            // density >= 25 %: move the whole covering row range with one DMA (at most 4 x chunk_in bytes,
+            // free on the otherwise idle H2D direction) instead of gathering the kept rows on the CPU
+            c.dense = cover_rows <= 4 * kept_rows;
             c.in_rows = c.dense ? cover_rows : kept_rows;
             c.out_off = out_before(line);
             c.out_bytes = out_before(b) - c.out_off;
@@ -739,18 +767,45 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
         }
     }
 
+    lap("planned");
     Job job;
     job.f = f; job.var_idx = var_idx; job.n_var = n_var; job.sam_idx = sam_idx; job.K = K;
     job.prefix_blob = prefix_blob; job.prefix_off = prefix_off; job.sink = sink;
     job.variant = (int)env_u64("PGB_K2_VARIANT", 0);
+    job.trace = trace;
+    job.t0 = t_begin;
 
     std::unique_ptr<WritePool> pool;
+    struct Unmap {
+        void *p = nullptr;
+        size_t n = 0;
+        ~Unmap() { if (p) munmap(p, n); }
+    } unmap;
     if ((sink->fd >= 0 && sink->positional) || (sink->mem && !sink->mem_pinned && total > (64u << 20))) {
         if (sink->fd >= 0) {
-            // regular file: size it once so that concurrent pwrite()s do not serialise on extending it
+            // regular file: size it once so that concurrent writers do not serialise on extending it
             struct stat st;
-            if (fstat(sink->fd, &st) == 0 && S_ISREG(st.st_mode) && (uint64_t)st.st_size < sink->base + total)
-                (void)!ftruncate(sink->fd, (off_t)(sink->base + total));
+            const bool regular = fstat(sink->fd, &st) == 0 && S_ISREG(st.st_mode);
+            if (regular && (uint64_t)st.st_size < sink->base + total) (void)!ftruncate(sink->fd, (off_t)(sink->base + total));
+            if (regular && total >= (64u << 20) && env_u64("PGB_MMAP_SINK", 1)) {
+                // map the body region; the caller's descriptor is usually write-only (File::create), which
+                // mmap(PROT_WRITE, MAP_SHARED) rejects, so reopen the same file read-write through /proc
+                char link[64];
+                snprintf(link, sizeof link, "/proc/self/fd/%d", sink->fd);
+                const int rw = open(link, O_RDWR);
+                if (rw >= 0) {
+                    const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE);
+                    const uint64_t lo = sink->base / page * page;
+                    const size_t len = (size_t)(sink->base + total - lo);
+                    void *m = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, rw, (off_t)lo);
+                    close(rw);
+                    if (m != MAP_FAILED) {
+                        unmap.p = m;
+                        unmap.n = len;
+                        sink->map = (uint8_t *)m + (sink->base - lo);
+                    }
+                }
+            }
         }
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
         const int n_writers = (int)env_u64("PGB_WRITERS", std::min<uint64_t>(8, std::max(1u, hw / 2)));
@@ -765,6 +820,7 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
         for (int g = 0; g < G; g++) th.emplace_back(run_device, &job, &work[g]);
         for (auto &t : th) t.join();
     }
+    lap("devices done");
     int rc = job.status.load();
     if (rc != PGB_OK) {
         pgb_set_error("%s", job.err);
