@@ -470,7 +470,7 @@ def run_b200(args, wl, rank, world, local_rank):
                     e2e_file = {"value": genotypes_step / tt, "unit": UNIT, "vcf_gb_per_s": total / tt / 1e9,
                                 "ms_per_step": 1e3 * tt, "sink": "regular file in %s (%s), no fsync" % (
                                     where, "tmpfs" if where == "/dev/shm" else "page cache"),
-                                "api": "pgb_export_gt_vcf (fd sink, parallel pwrite)", "chunks": int(stf.n_chunks),
+                                "api": "pgb_export_gt_vcf (fd sink; tmpfs: parallel copies through a mapping, else pwrite)", "chunks": int(stf.n_chunks),
                                 "roofline": {"bound": "storage", "achieved": total / tt / 1e9, "peak": pw_gbs, "unit": "GB/s",
                                              "frac": total / tt / 1e9 / pw_gbs,
                                              "peak_source": "single-thread pwrite of the same bytes to the same file system, measured in this run"}}
