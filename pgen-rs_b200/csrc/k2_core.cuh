@@ -180,7 +180,9 @@ PGB_DEV uint32_t pgb_chunk_codes(const uint8_t *row, const void *src, uint32_t s
            (pgb_code(row, s4) << 8);
 }
 
-template <bool GATHER, int HINT, int REPL>
+// ONE = the launch has one tile per line (every line fits in tile_bytes: the chr22 shapes), so
+// the clipping of every range to the tile [t0, t1) folds away at compile time.
+template <bool GATHER, int HINT, int REPL, bool ONE>
 PGB_DEV void pgb_k2_item(const pgb_k2_params &p, const pgb_line_meta &m, uint32_t tile, uint32_t lane,
                          const pgb_u4 *lut4) {
     constexpr int UNROLL = 4;
@@ -190,14 +192,17 @@ PGB_DEV void pgb_k2_item(const pgb_k2_params &p, const pgb_line_meta &m, uint32_
     const uint64_t a_gs = a_ls + P;
     const uint64_t a_ge = a_gs + K4;
     const uint64_t a_le = a_ge + 1;
-    const uint64_t t0 = (a_ls & ~511ull) + (uint64_t)tile * p.tile_bytes;
-    if (t0 >= a_le) return;
-    const uint64_t t1 = t0 + p.tile_bytes;
+    const uint64_t t0 = ONE ? 0ull : (a_ls & ~511ull) + (uint64_t)tile * p.tile_bytes;
+    if (!ONE && t0 >= a_le) return;
+    const uint64_t t1 = ONE ? ~0ull : t0 + p.tile_bytes;
     uint64_t b0 = (a_gs + 15ull) & ~15ull, b1 = a_ge & ~15ull;
     if (b0 >= b1) { b0 = a_le; b1 = a_le; } // no aligned chunk inside the GT text: bytes only
     const uint8_t *row = p.records + m.rec_off;
 
-    { // prefix bytes (pfile.rs:157-161)
+    if (ONE) { // prefix bytes (pfile.rs:157-161), line-relative 32-bit offsets
+        const uint8_t *pfx = p.prefix_blob + m.pfx_off;
+        for (uint32_t x = lane; x < P; x += 32) pgb_st8(a_ls + x, pgb_ld8(pfx + x));
+    } else {
         const uint8_t *pfx = p.prefix_blob + m.pfx_off;
         const uint64_t lo = a_ls > t0 ? a_ls : t0, hi = a_gs < t1 ? a_gs : t1;
         for (uint64_t a = lo + lane; a < hi; a += 32) pgb_st8(a, pgb_ld8(pfx + (a - a_ls)));
@@ -207,7 +212,7 @@ PGB_DEV void pgb_k2_item(const pgb_k2_params &p, const pgb_line_meta &m, uint32_
         // newline (pfile.rs:190) behind the last one (lanes 16-31), in one pass
         const uint64_t a = lane < 16 ? a_gs + lane : b1 + (lane - 16u);
         const uint64_t end = lane < 16 ? b0 : a_le;
-        if (a < end && a >= t0 && a < t1) pgb_st8(a, pgb_gt_byte<GATHER>(p, row, K4, a - a_gs));
+        if (a < end && (ONE || (a >= t0 && a < t1))) pgb_st8(a, pgb_gt_byte<GATHER>(p, row, K4, a - a_gs));
     } else { // no aligned chunk inside the GT text: the whole GT region byte by byte
         const uint64_t lo = a_gs > t0 ? a_gs : t0, hi = a_le < t1 ? a_le : t1;
         for (uint64_t a = lo + lane; a < hi; a += 32) pgb_st8(a, pgb_gt_byte<GATHER>(p, row, K4, a - a_gs));

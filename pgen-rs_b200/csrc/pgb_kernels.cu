@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_emit(const uint32_t *__restrict
 constexpr int K2_THREADS = 256;
 constexpr int K2_WARPS = K2_THREADS / 32;
 
-template <bool GATHER, int HINT, int REPL, int IPW>
+template <bool GATHER, int HINT, int REPL, int IPW, bool ONE>
 __global__ void __launch_bounds__(K2_THREADS) k2_format_kernel(const pgb_k2_params p) {
     constexpr int ITEMS = K2_WARPS * IPW;
     __shared__ __align__(16) pgb_u4 s_lut4[256 * REPL];
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_format_kernel(const pgb_k2_para
         const uint32_t slot = j * K2_WARPS + warp;
         if (item0 + slot >= n_items) break;
         const pgb_line_meta m = s_meta[slot];
-        pgb_k2_item<GATHER, HINT, REPL>(p, m, s_tile[slot], lane, s_lut4);
+        pgb_k2_item<GATHER, HINT, REPL, ONE>(p, m, ONE ? 0u : s_tile[slot], lane, s_lut4);
     }
 }
 
@@ -393,8 +393,8 @@ extern "C" int pgb_dev_index_lines(const uint32_t *var_row, const uint64_t *pref
     return rc;
 }
 
-template <bool GATHER, int HINT, int REPL, int IPW>
-static int launch_k2(const pgb_k2_params &p, cudaStream_t st) {
+template <bool GATHER, int HINT, int REPL, int IPW, bool ONE>
+static int launch_k2_one(const pgb_k2_params &p, cudaStream_t st) {
     const uint64_t n_items = p.n_lines * (uint64_t)p.n_tiles;
     if (n_items == 0) return PGB_OK;
     const uint64_t per_cta = (uint64_t)K2_WARPS * IPW;
@@ -403,8 +403,14 @@ static int launch_k2(const pgb_k2_params &p, cudaStream_t st) {
         pgb_set_error("K2 grid of %llu CTAs exceeds the launch limit", (unsigned long long)blocks);
         return PGB_E_ARG;
     }
-    k2_format_kernel<GATHER, HINT, REPL, IPW><<<(unsigned)blocks, K2_THREADS, 0, st>>>(p);
+    k2_format_kernel<GATHER, HINT, REPL, IPW, ONE><<<(unsigned)blocks, K2_THREADS, 0, st>>>(p);
     return check_launch("k2_format_kernel");
+}
+
+template <bool GATHER, int HINT, int REPL, int IPW>
+static int launch_k2(const pgb_k2_params &p, cudaStream_t st) {
+    return p.n_tiles == 1 ? launch_k2_one<GATHER, HINT, REPL, IPW, true>(p, st)
+                          : launch_k2_one<GATHER, HINT, REPL, IPW, false>(p, st);
 }
 
 template <bool GATHER, int HINT, int REPL>

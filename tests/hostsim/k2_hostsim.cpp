@@ -52,13 +52,16 @@ extern "C" int sim_format_lines(const uint8_t *records, uint64_t pitch, const ui
     for (uint64_t line = 0; line < n_lines; line++)
         for (uint32_t tile = 0; tile < p.n_tiles; tile++)
             for (uint32_t lane = 0; lane < 32; lane++) {
+                const bool one = p.n_tiles == 1;
+#define SIM(G, R)                                                                        \
+    (one ? pgb_k2_item<G, 0, R, true>(p, meta[line], tile, lane, lut4.data())            \
+         : pgb_k2_item<G, 0, R, false>(p, meta[line], tile, lane, lut4.data()))
                 if (!single) {
-                    if (g) pgb_k2_item<true, 0, 1>(p, meta[line], tile, lane, lut4.data());
-                    else pgb_k2_item<false, 0, 1>(p, meta[line], tile, lane, lut4.data());
+                    if (g) SIM(true, 1); else SIM(false, 1);
                 } else {
-                    if (g) pgb_k2_item<true, 0, 8>(p, meta[line], tile, lane, lut4.data());
-                    else pgb_k2_item<false, 0, 8>(p, meta[line], tile, lane, lut4.data());
+                    if (g) SIM(true, 8); else SIM(false, 8);
                 }
+#undef SIM
             }
     (void)hint;
     return 0;
