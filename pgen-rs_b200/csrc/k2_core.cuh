@@ -47,6 +47,7 @@ struct pgb_k2_params {
     uint32_t n_tiles;    // tiles per line
     uint32_t tile_bytes; // multiple of 512
     uint32_t row_bytes_hint; // keep-all: bytes of a record worth prefetching (R + 1)
+    uint32_t kidx_vec;       // kidx is 16-byte aligned: index reads may be vectorised
 };
 
 struct pgb_u4 {
@@ -71,6 +72,7 @@ PGB_DEV uint32_t pgb_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {
 }
 PGB_DEV uint32_t pgb_ld8(const uint8_t *p) { return *p; }
 PGB_DEV uint32_t pgb_ld32(const uint32_t *p) { return *p; }
+PGB_DEV pgb_u4 pgb_ld128(const uint32_t *p) { pgb_u4 r = {p[0], p[1], p[2], p[3]}; return r; }
 PGB_DEV pgb_line_meta pgb_ld_meta(const pgb_line_meta *p) { return *p; }
 PGB_DEV void pgb_st8(uint64_t a, uint32_t v) { *(uint8_t *)(uintptr_t)a = (uint8_t)v; }
 PGB_DEV void pgb_st16(uint64_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w, int) {
@@ -85,6 +87,11 @@ PGB_DEV uint32_t pgb_prmt(uint32_t x, uint32_t y, uint32_t s) { return __byte_pe
 PGB_DEV uint32_t pgb_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_r(lo, hi, sh); }
 PGB_DEV uint32_t pgb_ld8(const uint8_t *p) { return __ldg(p); }
 PGB_DEV uint32_t pgb_ld32(const uint32_t *p) { return __ldg(p); }
+PGB_DEV pgb_u4 pgb_ld128(const uint32_t *p) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+    pgb_u4 r = {v.x, v.y, v.z, v.w};
+    return r;
+}
 PGB_DEV pgb_line_meta pgb_ld_meta(const pgb_line_meta *p) {
     const uint4 *q = reinterpret_cast<const uint4 *>(p);
     uint4 a = __ldg(q), b = __ldg(q + 1);
@@ -167,15 +174,29 @@ PGB_DEV void pgb_emit_chunk(uint64_t A, uint32_t w, uint32_t r8, const pgb_u4 *l
 // The 10 code bits (5 fields) of a 16-byte chunk.  Keep-all: `src` points at the record byte
 // holding the chunk's first field (row + (q >> 4)), sh = 2-bit phase.  Gather: `src` points at
 // the chunk's first kept-sample index (kidx + (q >> 2); kidx is padded by 8 entries).
-template <bool GATHER>
+template <bool GATHER, bool VEC = false>
 PGB_DEV uint32_t pgb_chunk_codes(const uint8_t *row, const void *src, uint32_t sh) {
     if (!GATHER) {
         const uint8_t *b = (const uint8_t *)src;
         return pgb_prmt(pgb_ld8(b), pgb_ld8(b + 1), 0x1140u) >> sh;
     }
     const uint32_t *ki = (const uint32_t *)src;
-    const uint32_t s0 = pgb_ld32(ki), s1 = pgb_ld32(ki + 1), s2 = pgb_ld32(ki + 2), s3 = pgb_ld32(ki + 3);
-    const uint32_t s4 = pgb_ld32(ki + 4);
+    uint32_t s0, s1, s2, s3, s4;
+    if (VEC) {
+        // the chunk's first field f0 is congruent to j = sh / 2 modulo 4 for every chunk of the line, so
+        // the five indices sit at offset j of two aligned 16-byte reads (kidx is 16-byte aligned)
+        const uint32_t j = sh >> 1; // warp-uniform
+        const pgb_u4 a = pgb_ld128(ki - j), b = pgb_ld128(ki - j + 4);
+        switch (j) {
+        case 0: s0 = a.x; s1 = a.y; s2 = a.z; s3 = a.w; s4 = b.x; break;
+        case 1: s0 = a.y; s1 = a.z; s2 = a.w; s3 = b.x; s4 = b.y; break;
+        case 2: s0 = a.z; s1 = a.w; s2 = b.x; s3 = b.y; s4 = b.z; break;
+        default: s0 = a.w; s1 = b.x; s2 = b.y; s3 = b.z; s4 = b.w; break;
+        }
+    } else {
+        s0 = pgb_ld32(ki); s1 = pgb_ld32(ki + 1); s2 = pgb_ld32(ki + 2); s3 = pgb_ld32(ki + 3);
+        s4 = pgb_ld32(ki + 4);
+    }
     return pgb_code(row, s0) | (pgb_code(row, s1) << 2) | (pgb_code(row, s2) << 4) | (pgb_code(row, s3) << 6) |
            (pgb_code(row, s4) << 8);
 }
@@ -235,8 +256,14 @@ PGB_DEV void pgb_k2_item(const pgb_k2_params &p, const pgb_line_meta &m, uint32_
             const bool two = c + 32 < n_chunks;
             const void *sa = GATHER ? (const void *)(p.kidx + (qa >> 2)) : (const void *)(row + (qa >> 4));
             const void *sb = GATHER ? (const void *)(p.kidx + (qb >> 2)) : (const void *)(row + (qb >> 4));
-            const uint32_t wa = pgb_chunk_codes<GATHER>(row, sa, sh);
-            const uint32_t wb = two ? pgb_chunk_codes<GATHER>(row, sb, sh) : 0u;
+            uint32_t wa, wb = 0u;
+            if (GATHER && p.kidx_vec) {
+                wa = pgb_chunk_codes<GATHER, true>(row, sa, sh);
+                if (two) wb = pgb_chunk_codes<GATHER, true>(row, sb, sh);
+            } else {
+                wa = pgb_chunk_codes<GATHER>(row, sa, sh);
+                if (two) wb = pgb_chunk_codes<GATHER>(row, sb, sh);
+            }
             pgb_emit_chunk<REPL>(lo + 16ull * c, wa, r8, l4, HINT);
             if (two) pgb_emit_chunk<REPL>(lo + 16ull * c + 512u, wb, r8, l4, HINT);
         }

@@ -452,6 +452,7 @@ extern "C" int pgb_dev_format_lines(const uint8_t *records, const pgb_line_meta 
     p.n_tiles = (uint32_t)nt;
     // bytes of a record worth prefetching: all of it for keep-all, up to the last kept sample otherwise
     p.row_bytes_hint = kidx ? 0u : (n_kept + 3u) / 4u + 1u;
+    p.kidx_vec = kidx && ((uintptr_t)kidx & 15u) == 0 ? 1u : 0u;
     cudaStream_t st = (cudaStream_t)stream;
     const bool g = kidx != nullptr;
     if (hint == 1) {

@@ -43,6 +43,7 @@ extern "C" int sim_format_lines(const uint8_t *records, uint64_t pitch, const ui
     const uint64_t max_line = (uint64_t)maxp + 4ull * K + 1ull;
     p.n_tiles = (uint32_t)((max_line + 511ull + p.tile_bytes - 1) / p.tile_bytes);
     p.row_bytes_hint = 0;
+    p.kidx_vec = kidx && ((variant >> 4) & 1) ? 1u : 0u; // exercise both index-read forms
     // the tables the kernel builds in shared memory
     const int repl = single ? 8 : 1;
     std::vector<pgb_u4> lut4(256 * repl);
