@@ -473,7 +473,8 @@ def run_b200(args, wl, rank, world, local_rank):
                                 "api": "pgb_export_gt_vcf (fd sink; tmpfs: parallel copies through a mapping, else pwrite)", "chunks": int(stf.n_chunks),
                                 "roofline": {"bound": "storage", "achieved": total / tt / 1e9, "peak": pw_gbs, "unit": "GB/s",
                                              "frac": total / tt / 1e9 / pw_gbs,
-                                             "peak_source": "single-thread pwrite of the same bytes to the same file system, measured in this run"}}
+                                             "peak_source": "reference point, not a ceiling: ONE thread pwrite()ing the same bytes to the same "
+                                                            "file system, measured in this run (parallel writers can exceed it)"}}
                 finally:
                     if os.path.exists(path):
                         os.unlink(path)

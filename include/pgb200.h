@@ -195,8 +195,12 @@ int pgb_dev_index_lines(const uint32_t *var_row, const uint64_t *prefix_off, uin
                         uint32_t n_kept, uint64_t pitch, pgb_line_meta *meta, void *scratch, void *stream);
 
 /* K2: decode + gather + format.  kidx NULL => all n_samples samples (n_kept must equal
- * n_samples); otherwise n_kept entries (+8 padding).  `records` must be readable for 16
- * bytes past its last record.  variant selects a tuning variant (0 = default). */
+ * n_samples); otherwise n_kept entries (+8 padding; vectorised reads when 16-byte aligned).
+ * `records` must be readable for 16 bytes past its last record, and the 128-byte-aligned
+ * blocks containing its first and last byte must lie inside the allocation (true for any
+ * pointer into a cudaMalloc allocation): K2 prefetches record slices by cache line.
+ * variant = 0 selects the measured-best configuration; other values are tuning knobs
+ * (store hint, LUT copies, items per warp, tile size — see pgb_kernels.cu). */
 int pgb_dev_format_lines(const uint8_t *records, const pgb_line_meta *meta, uint64_t n_lines,
                          const uint8_t *prefix_blob, const uint32_t *kidx, uint32_t n_kept, uint32_t max_prefix_len,
                          uint8_t *out, int variant, void *stream);

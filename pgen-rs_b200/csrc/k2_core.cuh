@@ -80,7 +80,6 @@ PGB_DEV void pgb_st16(uint64_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w
     memcpy((void *)(uintptr_t)a, t, 16);
 }
 PGB_DEV pgb_u4 pgb_lds4(const pgb_u4 *e) { return *e; }
-PGB_DEV uint32_t pgb_lds1(const uint32_t *e) { return *e; }
 #else
 #define PGB_DEV __device__ __forceinline__
 PGB_DEV uint32_t pgb_prmt(uint32_t x, uint32_t y, uint32_t s) { return __byte_perm(x, y, s); }
@@ -119,7 +118,6 @@ PGB_DEV pgb_u4 pgb_lds4(const pgb_u4 *e) {
     pgb_u4 r = {v.x, v.y, v.z, v.w};
     return r;
 }
-PGB_DEV uint32_t pgb_lds1(const uint32_t *e) { return *e; }
 #endif
 
 // Little-endian text word of one genotype field: '\t', a, '/', b  (pfile.rs:177-188).
