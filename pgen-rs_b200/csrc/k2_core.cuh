@@ -199,45 +199,12 @@ PGB_DEV uint32_t pgb_chunk_codes(const uint8_t *row, const void *src, uint32_t s
            (pgb_code(row, s4) << 8);
 }
 
-// ONE = the launch has one tile per line (every line fits in tile_bytes: the chr22 shapes), so
-// the clipping of every range to the tile [t0, t1) folds away at compile time.
-template <bool GATHER, int HINT, int REPL, bool ONE>
-PGB_DEV void pgb_k2_item(const pgb_k2_params &p, const pgb_line_meta &m, uint32_t tile, uint32_t lane,
-                         const pgb_u4 *lut4) {
+// The aligned body [lo, hi) of a line's GT text (16-byte chunks, every one wholly inside the
+// text): short bodies chunk-indexed, long ones in 512-byte-aligned software-pipelined rows.
+template <bool GATHER, int HINT, int REPL>
+PGB_DEV void pgb_k2_body(const pgb_k2_params &p, const uint8_t *row, uint64_t a_gs, uint64_t lo, uint64_t hi,
+                         uint32_t lane, const pgb_u4 *lut4) {
     constexpr int UNROLL = 4;
-    const uint32_t P = m.pfx_len;
-    const uint64_t K4 = 4ull * p.K;
-    const uint64_t a_ls = (uint64_t)(uintptr_t)p.out + m.line_off;
-    const uint64_t a_gs = a_ls + P;
-    const uint64_t a_ge = a_gs + K4;
-    const uint64_t a_le = a_ge + 1;
-    const uint64_t t0 = ONE ? 0ull : (a_ls & ~511ull) + (uint64_t)tile * p.tile_bytes;
-    if (!ONE && t0 >= a_le) return;
-    const uint64_t t1 = ONE ? ~0ull : t0 + p.tile_bytes;
-    uint64_t b0 = (a_gs + 15ull) & ~15ull, b1 = a_ge & ~15ull;
-    if (b0 >= b1) { b0 = a_le; b1 = a_le; } // no aligned chunk inside the GT text: bytes only
-    const uint8_t *row = p.records + m.rec_off;
-
-    if (ONE) { // prefix bytes (pfile.rs:157-161), line-relative 32-bit offsets
-        const uint8_t *pfx = p.prefix_blob + m.pfx_off;
-        for (uint32_t x = lane; x < P; x += 32) pgb_st8(a_ls + x, pgb_ld8(pfx + x));
-    } else {
-        const uint8_t *pfx = p.prefix_blob + m.pfx_off;
-        const uint64_t lo = a_ls > t0 ? a_ls : t0, hi = a_gs < t1 ? a_gs : t1;
-        for (uint64_t a = lo + lane; a < hi; a += 32) pgb_st8(a, pgb_ld8(pfx + (a - a_ls)));
-    }
-    if (b0 < b1) {
-        // <= 15 GT bytes in front of the first aligned chunk (lanes 0-15) and <= 15 GT bytes + the
-        // newline (pfile.rs:190) behind the last one (lanes 16-31), in one pass
-        const uint64_t a = lane < 16 ? a_gs + lane : b1 + (lane - 16u);
-        const uint64_t end = lane < 16 ? b0 : a_le;
-        if (a < end && (ONE || (a >= t0 && a < t1))) pgb_st8(a, pgb_gt_byte<GATHER>(p, row, K4, a - a_gs));
-    } else { // no aligned chunk inside the GT text: the whole GT region byte by byte
-        const uint64_t lo = a_gs > t0 ? a_gs : t0, hi = a_le < t1 ? a_le : t1;
-        for (uint64_t a = lo + lane; a < hi; a += 32) pgb_st8(a, pgb_gt_byte<GATHER>(p, row, K4, a - a_gs));
-    }
-    const uint64_t lo = b0 > t0 ? b0 : t0, hi = b1 < t1 ? b1 : t1;
-    if (lo >= hi) return;
 
     const uint32_t delta = (uint32_t)(0ull - a_gs) & 15u; // (A - a_gs) & 15 for any 16-aligned A
     const uint32_t r8 = (delta & 3u) * 8u;                // byte phase inside a field, in bits
@@ -350,4 +317,107 @@ PGB_DEV void pgb_k2_item(const pgb_k2_params &p, const pgb_line_meta &m, uint32_
     }
     for (; rowA < hi; rowA += 512, A += 512, src += STEP)
         if (A < hi) pgb_emit_chunk<REPL>(A, pgb_chunk_codes<GATHER>(row, src, sh), r8, l4, HINT);
+}
+
+// One (line, tile) item of a launch whose lines are cut into tiles (wide lines: 500 000 samples =
+// 2 MB of text): every range is clipped to the tile [t0, t1).
+template <bool GATHER, int HINT, int REPL>
+PGB_DEV void pgb_k2_item(const pgb_k2_params &p, const pgb_line_meta &m, uint32_t tile, uint32_t lane,
+                         const pgb_u4 *lut4) {
+    const uint32_t P = m.pfx_len;
+    const uint64_t K4 = 4ull * p.K;
+    const uint64_t a_ls = (uint64_t)(uintptr_t)p.out + m.line_off;
+    const uint64_t a_gs = a_ls + P;
+    const uint64_t a_ge = a_gs + K4;
+    const uint64_t a_le = a_ge + 1;
+    const uint64_t t0 = (a_ls & ~511ull) + (uint64_t)tile * p.tile_bytes;
+    if (t0 >= a_le) return;
+    const uint64_t t1 = t0 + p.tile_bytes;
+    uint64_t b0 = (a_gs + 15ull) & ~15ull, b1 = a_ge & ~15ull;
+    if (b0 >= b1) { b0 = a_le; b1 = a_le; } // no aligned chunk inside the GT text: bytes only
+    const uint8_t *row = p.records + m.rec_off;
+
+    { // prefix bytes (pfile.rs:157-161)
+        const uint8_t *pfx = p.prefix_blob + m.pfx_off;
+        const uint64_t lo = a_ls > t0 ? a_ls : t0, hi = a_gs < t1 ? a_gs : t1;
+        for (uint64_t a = lo + lane; a < hi; a += 32) pgb_st8(a, pgb_ld8(pfx + (a - a_ls)));
+    }
+    if (b0 < b1) {
+        // <= 15 GT bytes in front of the first aligned chunk (lanes 0-15) and <= 15 GT bytes + the
+        // newline (pfile.rs:190) behind the last one (lanes 16-31), in one pass
+        const uint64_t a = lane < 16 ? a_gs + lane : b1 + (lane - 16u);
+        const uint64_t end = lane < 16 ? b0 : a_le;
+        if (a < end && a >= t0 && a < t1) pgb_st8(a, pgb_gt_byte<GATHER>(p, row, K4, a - a_gs));
+    } else { // no aligned chunk inside the GT text: the whole GT region byte by byte
+        const uint64_t lo = a_gs > t0 ? a_gs : t0, hi = a_le < t1 ? a_le : t1;
+        for (uint64_t a = lo + lane; a < hi; a += 32) pgb_st8(a, pgb_gt_byte<GATHER>(p, row, K4, a - a_gs));
+    }
+    const uint64_t lo = b0 > t0 ? b0 : t0, hi = b1 < t1 ? b1 : t1;
+    if (lo < hi) pgb_k2_body<GATHER, HINT, REPL>(p, row, a_gs, lo, hi, lane, lut4);
+}
+
+// One-byte GT lookup with line-relative 32-bit offsets (g = offset from the start of the GT text).
+template <bool GATHER>
+PGB_DEV uint32_t pgb_gt_byte32(const pgb_k2_params &p, const uint8_t *row, uint32_t K4, uint32_t g) {
+    if (g >= K4) return '\n';
+    const uint32_t f = g >> 2;
+    const uint32_t s = GATHER ? pgb_ld32(p.kidx + f) : f;
+    return (pgb_gt_word(pgb_code(row, s)) >> ((g & 3u) * 8u)) & 0xFFu;
+}
+
+// A whole line in one item (launches whose every line fits in tile_bytes: the chr22 shapes).
+// Same bytes as pgb_k2_item, but every position is a 32-bit offset x from the line start
+// (address = a_ls + x), there is no tile to clip against, and the short body keeps one 64-bit
+// store pointer per lane — the per-line bookkeeping is what bounds short lines (ncu: 395 warp
+// instructions per 1 041-byte line on the gather workload before this path existed).
+template <bool GATHER, int HINT, int REPL>
+PGB_DEV void pgb_k2_line(const pgb_k2_params &p, const pgb_line_meta &m, uint32_t lane, const pgb_u4 *lut4) {
+    const uint32_t P = m.pfx_len;
+    const uint32_t K4 = 4u * p.K; // < tile_bytes <= 128 MiB
+    const uint64_t a_ls = (uint64_t)(uintptr_t)p.out + m.line_off;
+    const uint32_t al = (uint32_t)a_ls & 15u;
+    const uint32_t x_gs = P, x_ge = P + K4, x_le = x_ge + 1u;
+    const uint8_t *row = p.records + m.rec_off;
+    { // prefix bytes (pfile.rs:157-161)
+        const uint8_t *pfx = p.prefix_blob + m.pfx_off;
+        for (uint32_t x = lane; x < P; x += 32) pgb_st8(a_ls + x, pgb_ld8(pfx + x));
+    }
+    // [xb0, xb1): the part of the GT text made of whole 16-byte-aligned chunks
+    const uint32_t yb0 = (al + x_gs + 15u) & ~15u, yb1 = (al + x_ge) & ~15u; // relative to a_ls - al
+    const uint32_t xb0 = yb0 - al, xb1 = yb1 - al;                          // (xb1 is only used when yb0 < yb1)
+    if (yb0 >= yb1) { // none: the GT text and the newline byte by byte
+        for (uint32_t x = x_gs + lane; x < x_le; x += 32) pgb_st8(a_ls + x, pgb_gt_byte32<GATHER>(p, row, K4, x - x_gs));
+        return;
+    }
+    { // <= 15 GT bytes in front (lanes 0-15), <= 15 GT bytes + the newline behind (lanes 16-31)
+        const uint32_t x = lane < 16 ? x_gs + lane : xb1 + (lane - 16u);
+        const uint32_t end = lane < 16 ? xb0 : x_le;
+        if (x < end) pgb_st8(a_ls + x, pgb_gt_byte32<GATHER>(p, row, K4, x - x_gs));
+    }
+    const uint32_t n_chunks = (xb1 - xb0) >> 4;
+    if (n_chunks > 128u) { // long body: the row-aligned pipelined path
+        pgb_k2_body<GATHER, HINT, REPL>(p, row, a_ls + x_gs, a_ls + xb0, a_ls + xb1, lane, lut4);
+        return;
+    }
+    const uint32_t delta = (0u - (al + x_gs)) & 15u; // (A - a_gs) & 15 for any 16-aligned A
+    const uint32_t r8 = (delta & 3u) * 8u;
+    const uint32_t sh = (delta >> 2) * 2u;
+    const pgb_u4 *l4 = lut4 + (lane & (uint32_t)(REPL - 1));
+    uint64_t A = a_ls + xb0 + 16u * lane; // this lane's first chunk
+    uint32_t q = xb0 - x_gs + 16u * lane; // its GT offset
+    for (uint32_t c = lane; c < n_chunks; c += 64, A += 1024, q += 1024) {
+        const bool two = c + 32 < n_chunks;
+        const void *sa = GATHER ? (const void *)(p.kidx + (q >> 2)) : (const void *)(row + (q >> 4));
+        const void *sb = GATHER ? (const void *)(p.kidx + ((q + 512u) >> 2)) : (const void *)(row + ((q + 512u) >> 4));
+        uint32_t wa, wb = 0u;
+        if (GATHER && p.kidx_vec) {
+            wa = pgb_chunk_codes<GATHER, true>(row, sa, sh);
+            if (two) wb = pgb_chunk_codes<GATHER, true>(row, sb, sh);
+        } else {
+            wa = pgb_chunk_codes<GATHER>(row, sa, sh);
+            if (two) wb = pgb_chunk_codes<GATHER>(row, sb, sh);
+        }
+        pgb_emit_chunk<REPL>(A, wa, r8, l4, HINT);
+        if (two) pgb_emit_chunk<REPL>(A + 512u, wb, r8, l4, HINT);
+    }
 }

@@ -222,10 +222,20 @@ __global__ void __launch_bounds__(K2_THREADS) k2_format_kernel(const pgb_k2_para
             s_tile[threadIdx.x] = tile;
         }
     }
-    {
-        const pgb_u4 e = pgb_lut_entry(threadIdx.x);
+    if (REPL == 1) {
+        s_lut4[threadIdx.x] = pgb_lut_entry(threadIdx.x);
+    } else {
+        // REPL interleaved copies, written without bank conflicts: stage one copy, then thread t
+        // fills slots t, t + 256, ... (slot = entry * REPL + copy), consecutive lanes -> consecutive
+        // 16-byte slots.
+        __shared__ __align__(16) pgb_u4 s_one[REPL > 1 ? 256 : 1];
+        s_one[threadIdx.x] = pgb_lut_entry(threadIdx.x);
+        __syncthreads();
 #pragma unroll
-        for (int g = 0; g < REPL; g++) s_lut4[threadIdx.x * REPL + g] = e;
+        for (int k = 0; k < REPL; k++) {
+            const uint32_t slot = threadIdx.x + 256u * k;
+            s_lut4[slot] = s_one[slot / REPL];
+        }
     }
     __syncthreads();
     { // L2 prefetch: 8 threads per item walk the 128-byte lines of its record slice and prefix
@@ -270,7 +280,8 @@ __global__ void __launch_bounds__(K2_THREADS) k2_format_kernel(const pgb_k2_para
         const uint32_t slot = j * K2_WARPS + warp;
         if (item0 + slot >= n_items) break;
         const pgb_line_meta m = s_meta[slot];
-        pgb_k2_item<GATHER, HINT, REPL, ONE>(p, m, ONE ? 0u : s_tile[slot], lane, s_lut4);
+        if (ONE) pgb_k2_line<GATHER, HINT, REPL>(p, m, lane, s_lut4);
+        else pgb_k2_item<GATHER, HINT, REPL>(p, m, s_tile[slot], lane, s_lut4);
     }
 }
 
@@ -415,7 +426,7 @@ static int launch_k2(const pgb_k2_params &p, cudaStream_t st) {
 
 template <bool GATHER, int HINT, int REPL>
 static int launch_k2_ipw(const pgb_k2_params &p, cudaStream_t st, int ipw) {
-    if (ipw == 0) ipw = GATHER ? 4 : 2; // measured best on the chr22 shapes (profiles/README.md)
+    if (ipw == 0) ipw = GATHER ? 4 : 1; // measured best on the chr22 shapes (profiles/README.md)
     switch (ipw) {
     case 1: return launch_k2<GATHER, HINT, REPL, 1>(p, st);
     case 2: return launch_k2<GATHER, HINT, REPL, 2>(p, st);
@@ -425,8 +436,9 @@ static int launch_k2_ipw(const pgb_k2_params &p, cudaStream_t st, int ipw) {
 }
 
 // variant: bits 0-3  store hint (0 => .cs streaming, the measured best; 2 => default write-back)
-//          bits 4-7  LUT copies (0 => one copy; 1 => 8 interleaved bank-conflict-free copies)
-//          bits 8-11 items per warp (0 => 2 keep-all / 4 gather; 1, 2, 4, 8)
+//          bits 4-7  LUT copies (0 => default: 8 interleaved bank-conflict-free copies for keep-all, one
+//                    copy for gather; 1 => 8 copies; 2 => one copy)
+//          bits 8-11 items per warp (0 => 1 keep-all / 4 gather; 1, 2, 4, 8)
 //          bits 12-15 tile size = 4 KiB << n (0 => 16 KiB)
 extern "C" int pgb_dev_format_lines(const uint8_t *records, const pgb_line_meta *meta, uint64_t n_lines,
                                     const uint8_t *prefix_blob, const uint32_t *kidx, uint32_t n_kept,
@@ -442,7 +454,8 @@ extern "C" int pgb_dev_format_lines(const uint8_t *records, const pgb_line_meta 
     p.n_lines = n_lines;
     p.K = n_kept;
     const int hint = (variant & 0xF) == 2 ? 0 : 1;
-    const int repl8 = (variant >> 4) & 0xF;
+    const int lsel = (variant >> 4) & 0xF;
+    const bool repl8 = lsel == 1 || (lsel == 0 && kidx == nullptr);
     const int ipw = (variant >> 8) & 0xF;
     const int tsel = (variant >> 12) & 0xF;
     p.tile_bytes = tsel ? (4096u << tsel) : 16384u;

@@ -37,13 +37,14 @@ extern "C" int sim_format_lines(const uint8_t *records, uint64_t pitch, const ui
     p.n_lines = n_lines;
     p.K = K;
     const int hint = variant & 0xF;
-    const int single = (variant >> 4) & 0xF;
+    const int lsel = (variant >> 4) & 0xF;
+    const int single = lsel == 1 || (lsel == 0 && kidx == nullptr); // 1 => 8 LUT copies
     const int tsel = (variant >> 12) & 0xF;
     p.tile_bytes = tsel ? (4096u << tsel) : 16384u;
     const uint64_t max_line = (uint64_t)maxp + 4ull * K + 1ull;
     p.n_tiles = (uint32_t)((max_line + 511ull + p.tile_bytes - 1) / p.tile_bytes);
     p.row_bytes_hint = 0;
-    p.kidx_vec = kidx && ((variant >> 4) & 1) ? 1u : 0u; // exercise both index-read forms
+    p.kidx_vec = kidx && (variant & 1) == 0 ? 1u : 0u; // exercise both index-read forms
     // the tables the kernel builds in shared memory
     const int repl = single ? 8 : 1;
     std::vector<pgb_u4> lut4(256 * repl);
@@ -55,8 +56,8 @@ extern "C" int sim_format_lines(const uint8_t *records, uint64_t pitch, const ui
             for (uint32_t lane = 0; lane < 32; lane++) {
                 const bool one = p.n_tiles == 1;
 #define SIM(G, R)                                                                        \
-    (one ? pgb_k2_item<G, 0, R, true>(p, meta[line], tile, lane, lut4.data())            \
-         : pgb_k2_item<G, 0, R, false>(p, meta[line], tile, lane, lut4.data()))
+    (one ? pgb_k2_line<G, 0, R>(p, meta[line], lane, lut4.data())                        \
+         : pgb_k2_item<G, 0, R>(p, meta[line], tile, lane, lut4.data()))
                 if (!single) {
                     if (g) SIM(true, 1); else SIM(false, 1);
                 } else {

@@ -54,7 +54,7 @@ def test_golden_vectors_through_pfile_api(pgb, kat_cases, tmp_path):
         assert open(out, "rb").read() == case["vcf"].encode(), case["name"]
 
 
-@pytest.mark.parametrize("variant", [0x000, 0x010, 0x002, 0x112, 0x1200, 0x2812])
+@pytest.mark.parametrize("variant", [0x000, 0x010, 0x020, 0x112, 0x222, 0x1410, 0x2822])
 def test_random_shapes_bit_exact(pgb, variant, monkeypatch):
     monkeypatch.setenv("PGB_K2_VARIANT", str(variant))
     rng = np.random.default_rng(variant + 5)

@@ -8,7 +8,7 @@ import pytest
 import oracle_np as onp
 import synth
 
-VARIANTS = [0x000, 0x010, 0x001, 0x011, 0x1000, 0x1010, 0x2000]
+VARIANTS = [0x000, 0x010, 0x020, 0x001, 0x011, 0x021, 0x1000, 0x1010, 0x2020]
 
 
 def run_sim(k2sim, rng, n, m, k_sel, var_sel, plen, phase, variant):
