@@ -415,3 +415,34 @@ def test_multi_device_sharding_matches_single(pgb, monkeypatch):
     with pgb.PgenFile(image=image_of(recs, n)) as f:
         for devs in ([0, 1], list(range(ndev))):
             assert pgb.export_to_bytes(f, None, None, blob, off, devices=devs) == want
+
+
+def test_concurrent_exports_share_device_buffers(pgb):
+    """Two host threads exporting at once on one device: the process-wide device buffers are leased
+    to one export at a time, so both must come out right; pgb_release_buffers() then frees them and
+    the next export re-creates them."""
+    import threading
+    rng = np.random.default_rng(31)
+    jobs = []
+    for n, m in ((1001, 700), (2504, 300)):
+        recs = rng.integers(0, 256, size=(m, synth.record_size(n)), dtype=np.uint8)
+        pre, blob, off = random_prefixes(rng, m, 10, 80)
+        sam = np.sort(rng.choice(n, size=n // 3, replace=False)).astype(np.uint32)
+        jobs.append((recs, n, blob, off, sam, onp.format_body(recs, np.arange(m), sam, pre)))
+    got = [None, None]
+
+    def work(i):
+        recs, n, blob, off, sam, _ = jobs[i]
+        with pgb.PgenFile(image=image_of(recs, n)) as f:
+            for _ in range(5):
+                got[i] = pgb.export_to_bytes(f, None, sam, blob, off)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert got[0] == jobs[0][5] and got[1] == jobs[1][5]
+    pgb.lib.pgb_release_buffers()
+    work(0)
+    assert got[0] == jobs[0][5]
