@@ -356,6 +356,34 @@ PGB_DEV void pgb_k2_item(const pgb_k2_params &p, const pgb_line_meta &m, uint32_
     if (lo < hi) pgb_k2_body<GATHER, HINT, REPL>(p, row, a_gs, lo, hi, lane, lut4);
 }
 
+// Prefix bytes (pfile.rs:157-161): P bytes from src to the line start a_ls (al = a_ls & 15).
+// Short prefixes go byte by byte; from 64 bytes on (real 1000G .pvar rows average 163) the
+// destination-aligned 16-byte chunks are copied with aligned 32-bit source reads re-phased by the
+// source/destination misalignment (constant per line), and only the <= 15 bytes on either side are
+// byte stores.
+PGB_DEV void pgb_copy_prefix(const uint8_t *src, uint64_t a_ls, uint32_t al, uint32_t P, uint32_t lane, int hint) {
+    if (P < 64u) {
+        for (uint32_t x = lane; x < P; x += 32) pgb_st8(a_ls + x, pgb_ld8(src + x));
+        return;
+    }
+    const uint32_t xa0 = (16u - al) & 15u;          // first 16-byte-aligned destination offset
+    const uint32_t xa1 = ((al + P) & ~15u) - al;    // end of the last whole chunk (P >= 64: xa1 > xa0)
+    { // the ragged ends: lanes 0-15 in front, lanes 16-31 behind
+        const uint32_t x = lane < 16 ? lane : xa1 + (lane - 16u);
+        const uint32_t end = lane < 16 ? xa0 : P;
+        if (x < end) pgb_st8(a_ls + x, pgb_ld8(src + x));
+    }
+    const uint32_t mis = (uint32_t)(uintptr_t)(src + xa0) & 3u; // same for every chunk of the line
+    const uint32_t sh8 = mis * 8u;
+    for (uint32_t x = xa0 + 16u * lane; x < xa1; x += 512u) {
+        const uint32_t *w = (const uint32_t *)(src + x - mis); // 4-byte aligned
+        const uint32_t w0 = pgb_ld32(w), w1 = pgb_ld32(w + 1), w2 = pgb_ld32(w + 2), w3 = pgb_ld32(w + 3);
+        const uint32_t w4 = mis ? pgb_ld32(w + 4) : 0u; // its first byte is inside the prefix when mis != 0
+        pgb_st16(a_ls + x, pgb_funnel_r(w0, w1, sh8), pgb_funnel_r(w1, w2, sh8), pgb_funnel_r(w2, w3, sh8),
+                 pgb_funnel_r(w3, w4, sh8), hint);
+    }
+}
+
 // One-byte GT lookup with line-relative 32-bit offsets (g = offset from the start of the GT text).
 template <bool GATHER>
 PGB_DEV uint32_t pgb_gt_byte32(const pgb_k2_params &p, const uint8_t *row, uint32_t K4, uint32_t g) {
@@ -378,10 +406,7 @@ PGB_DEV void pgb_k2_line(const pgb_k2_params &p, const pgb_line_meta &m, uint32_
     const uint32_t al = (uint32_t)a_ls & 15u;
     const uint32_t x_gs = P, x_ge = P + K4, x_le = x_ge + 1u;
     const uint8_t *row = p.records + m.rec_off;
-    { // prefix bytes (pfile.rs:157-161)
-        const uint8_t *pfx = p.prefix_blob + m.pfx_off;
-        for (uint32_t x = lane; x < P; x += 32) pgb_st8(a_ls + x, pgb_ld8(pfx + x));
-    }
+    pgb_copy_prefix(p.prefix_blob + m.pfx_off, a_ls, al, P, lane, HINT);
     // [xb0, xb1): the part of the GT text made of whole 16-byte-aligned chunks
     const uint32_t yb0 = (al + x_gs + 15u) & ~15u, yb1 = (al + x_ge) & ~15u; // relative to a_ls - al
     const uint32_t xb0 = yb0 - al, xb1 = yb1 - al;                          // (xb1 is only used when yb0 < yb1)

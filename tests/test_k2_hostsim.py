@@ -27,7 +27,7 @@ def run_sim(k2sim, rng, n, m, k_sel, var_sel, plen, phase, variant):
         k = k_sel
         ki = np.concatenate([sidx, np.zeros(8, np.uint32)]).astype(np.uint32)
     pre = [bytes(rng.integers(33, 127, size=rng.integers(plen[0], plen[1] + 1), dtype=np.uint8)) for _ in vr]
-    blob = np.frombuffer(b"".join(pre) + b"\0", dtype=np.uint8).copy()
+    blob = np.frombuffer(b"".join(pre) + b"\0" * 8, dtype=np.uint8).copy()
     off = np.zeros(len(vr) + 1, np.uint64)
     off[1:] = np.cumsum([len(x) for x in pre])
     exp = onp.format_body(recs, vr, sidx, pre)
@@ -46,6 +46,13 @@ def test_every_phase_keep_all(k2sim):
         run_sim(k2sim, rng, 301, 3, None, None, (0, 37), phase, VARIANTS[phase % len(VARIANTS)])
 
 
+def test_every_phase_wide_prefix(k2sim):
+    """Prefixes >= 64 bytes take the vectorised copy: every destination phase x source misalignment."""
+    rng = np.random.default_rng(5)
+    for phase in range(0, 64):
+        run_sim(k2sim, rng, 77, 5, None if phase % 2 else 30, None, (64, 210), phase, VARIANTS[phase % len(VARIANTS)])
+
+
 def test_every_phase_gather(k2sim):
     rng = np.random.default_rng(2)
     for phase in range(0, 64):
@@ -60,7 +67,7 @@ def test_random_shapes(k2sim):
         m = int(rng.integers(1, 10))
         k_sel = None if rng.integers(0, 3) == 0 else int(rng.integers(0, n + 1))
         var_sel = None if rng.integers(0, 2) else int(rng.integers(1, m + 1))
-        plen = [(0, 0), (0, 5), (1, 40), (30, 200)][rng.integers(0, 4)]
+        plen = [(0, 0), (0, 5), (1, 40), (30, 200), (60, 70), (150, 400)][rng.integers(0, 6)]
         run_sim(k2sim, rng, n, m, k_sel, var_sel, plen, int(rng.integers(0, 512)), int(rng.choice(VARIANTS)))
 
 
