@@ -640,6 +640,13 @@ void run_device(Job *job, DeviceWork *w) {
         for (auto &s : w->ctx->slot)
             if (s.stream) cudaStreamSynchronize(s.stream);
     }
+    // The context outlives this export (process-wide cache): a producer that failed between claiming
+    // a slot and queueing it must not leave the slot marked busy for the next export.
+    {
+        std::lock_guard<std::mutex> lk(w->ctx->mu);
+        for (auto &s : w->ctx->slot) s.busy = false;
+    }
+    if (job->status.load() != PGB_OK) cudaGetLastError(); // clear a sticky non-fatal error state
 }
 
 int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint32_t *sam_idx, uint64_t n_sam,

@@ -466,3 +466,23 @@ def test_tiny_shapes_exhaustive_alignment(pgb):
                 got = pgb.export_to_bytes(f, None, sam, blob, off)
                 want = onp.format_body(recs, np.arange(m), np.arange(n) if sam is None else sam, pre)
                 assert got == want, (n, None if sam is None else sam.tolist())
+
+
+def test_failed_export_leaves_the_device_buffers_usable(pgb, tmp_path):
+    """An I/O failure in the sink (descriptor opened read-only) is PGB_E_IO; the cached per-device
+    buffers must then serve the next export normally."""
+    rng = np.random.default_rng(41)
+    n, m = 777, 900
+    recs = rng.integers(0, 256, size=(m, synth.record_size(n)), dtype=np.uint8)
+    pre, blob, off = random_prefixes(rng, m, 5, 40)
+    want = onp.format_body(recs, np.arange(m), np.arange(n), pre)
+    ro = str(tmp_path / "ro.vcf")
+    open(ro, "wb").close()
+    with pgb.PgenFile(image=image_of(recs, n)) as f:
+        for sink_flags in (os.O_RDONLY, os.O_RDONLY | os.O_APPEND):
+            fd = os.open(ro, sink_flags)
+            with pytest.raises(pgb.PgbError) as ei:
+                f.export_gt_vcf(None, None, blob, off, fd)
+            os.close(fd)
+            assert ei.value.status == pgb.E_IO
+            assert pgb.export_to_bytes(f, None, None, blob, off) == want
