@@ -85,6 +85,42 @@ def bench(workload, extra=()):
     return json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
 
 
+def cfg3_cli(td, orc):
+    """configs[2] as a user runs it: `pgen-b200 filter <prefix> -o out.vcf` on a pfile triple on disk
+    (lean 8-column .pvar), page cache warm, against the oracle's whole output_vcf on the same files."""
+    import torch
+    n, m = 2504, 1_100_000
+    R = synth.record_size(n)
+    prefix = os.path.join(td, "chr22")
+    dev = torch.empty(m * R + 64, dtype=torch.uint8, device="cuda")
+    assert pgb200.lib.pgb_dev_synth_records(dev.data_ptr(), R, 3, 0, m, n, torch.cuda.current_stream().cuda_stream) == 0
+    with open(prefix + ".pgen", "wb") as f:
+        f.write(synth.pgen_header(m, n))
+        f.write(dev[:m * R].cpu().numpy().tobytes())
+    del dev
+    synth.write_pvar(prefix + ".pvar", "lean", m, 3)
+    synth.write_psam(prefix + ".psam", n)
+    cli = os.path.join(ROOT, "bin", "pgen-b200")
+    out = os.path.join(td, "chr22.gpu.vcf")
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        subprocess.run([cli, "filter", prefix, "-o", out], check=True)
+        ts.append(time.perf_counter() - t0)
+    want = os.path.join(td, "chr22.cpu.vcf")
+    t0 = time.perf_counter()
+    rc = orc.orc_output_vcf(prefix.encode(), None, -1, None, -1, want.encode(), 0)
+    cpu_dt = time.perf_counter() - t0
+    assert rc == 0
+    exact = sha(out) == sha(want)
+    size = os.path.getsize(out)
+    os.unlink(want)
+    return {"config": "3 chr22 keep-all via the CLI (files in, file out)", "genotypes": n * m, "vcf_bytes": size,
+            "gpu_wall_s": min(ts[1:]), "gpu_first_run_s": ts[0], "gpu_device_ms": float("nan"), "cpu_oracle_s": cpu_dt,
+            "bit_exact": exact, "note": "whole process: CUDA context creation, .pvar/.psam parse, header, export, file write to "
+                                        + td + " (no fsync); CPU column = oracle whole output_vcf, reference-faithful I/O"}
+
+
 def cfg5_full():
     """All 200 000 variants x 500 000 samples: 25 GB page-locked .pgen image (synthesised on the device,
     copied to the host once), exported through pgb_export_gt_vcf into /dev/null."""
@@ -124,6 +160,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--skip-cfg5-full", action="store_true")
+    ap.add_argument("--skip-cli", action="store_true")
     a = ap.parse_args()
     orc = oracle()
     res = []
@@ -139,6 +176,8 @@ def main():
         synth.write_pvar(r1 + ".pvar", "random1", 200000, 2)
         synth.write_pgen(r1 + ".pgen", 2, 200000, 300)
         res.append(small_config("2 random1 full", r1, None, None, td, orc))
+        if not a.skip_cli:
+            res.append(cfg3_cli(td, orc))
     for name, wl in (("3 chr22 keep-all", "chr22"), ("4 chr22 gather", "gather"), ("5 biobank block", "biobank-block")):
         d = bench(wl, () if wl == "chr22" else ("--no-file",))
         d["config_name"] = name
