@@ -27,10 +27,12 @@
 // phase r = q & 3; (q & 15) is the same for every chunk of a line, so in the keep-all
 // case the chunk needs row bytes (q >> 4) and (q >> 4) + 1 shifted by a per-line constant.
 //
-// Instruction budget (round 1 ncu: the first version was ALU-bound at ~100 instructions per
-// 16-byte chunk): the chunk body is  2 LDG.U8, PRMT+SHF (the 10 code bits w), LOP+IMAD+
-// LDS.128 (4 text words from the LUT), SHF+LOP+IMAD+LDS.32 (the 5th word), 4 SHF (byte
-// re-phasing), STG.128 — with full rows unrolled without predicates.
+// Instruction budget (round-1 ncu: the first version was ALU-bound at ~100 instructions per
+// 16-byte chunk): the chunk body is 2 LDG.U8, PRMT+SHF (the 10 code bits w), LOP+IMAD+LDS.128
+// (four text words from the LUT), SHF+LOP+PRMT (the 5th field's word), 4 SHF (byte re-phasing),
+// STG.128.  Entry points: pgb_k2_line (a whole line per warp, 32-bit line-relative offsets;
+// launches whose lines fit in one tile) and pgb_k2_item (a 16 KiB tile of a wide line); both
+// end in pgb_k2_body.
 #pragma once
 #include <stdint.h>
 

@@ -730,7 +730,7 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
 
     lap("ctx leased");
     // ---- plan: contiguous line ranges per device balanced by output bytes, then chunks ----
-    const uint64_t chunk_out = env_u64("PGB_CHUNK_MB", 256) << 20;
+    const uint64_t chunk_out = env_u64("PGB_CHUNK_MB", 128) << 20; // 64..1024 MB measured within 3 % of each other
     const uint64_t chunk_in = env_u64("PGB_CHUNK_IN_MB", 128) << 20;
     auto out_before = [&](uint64_t i) { return (prefix_off[i] - prefix_off[0]) + i * fixed; };
     uint64_t seq = 0;
