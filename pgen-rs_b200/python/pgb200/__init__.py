@@ -14,7 +14,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_ROOT = os.path.abspath(os.path.join(_HERE, "..", ".."))
-LIB_PATH = os.path.join(PKG_ROOT, "lib", "libpgb200.so")
+# PGB_LIB: an alternative build of the same library (A/B comparisons of kernel variants on one box)
+LIB_PATH = os.environ.get("PGB_LIB") or os.path.join(PKG_ROOT, "lib", "libpgb200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -59,7 +59,7 @@ def test_random_shapes_bit_exact(pgb, variant, monkeypatch):
     monkeypatch.setenv("PGB_K2_VARIANT", str(variant))
     rng = np.random.default_rng(variant + 5)
     sizes = [1, 2, 3, 4, 5, 7, 8, 15, 16, 17, 31, 33, 63, 64, 65, 100, 127, 129, 300, 511, 1000, 2504, 5000, 20000]
-    for trial in range(40):
+    for trial in range(int(os.environ.get("PGB_SOAK_TRIALS", "40"))):  # PGB_SOAK_TRIALS=2000 for a soak run
         n = int(rng.choice(sizes))
         m = int(rng.integers(1, 40))
         recs = rng.integers(0, 256, size=(m, synth.record_size(n)), dtype=np.uint8)
