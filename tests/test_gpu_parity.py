@@ -486,3 +486,21 @@ def test_failed_export_leaves_the_device_buffers_usable(pgb, tmp_path):
             os.close(fd)
             assert ei.value.status == pgb.E_IO
             assert pgb.export_to_bytes(f, None, None, blob, off) == want
+
+
+def test_variant_order_is_the_callers(pgb, monkeypatch):
+    """var_idx is written in the order given (the reference always passes ascending rows, but the
+    ABI does not require it): shuffled and descending selections, in one chunk and in many."""
+    rng = np.random.default_rng(55)
+    n, m = 1203, 3000
+    recs = rng.integers(0, 256, size=(m, synth.record_size(n)), dtype=np.uint8)
+    with pgb.PgenFile(image=image_of(recs, n)) as f:
+        for chunk_mb in ("128", "1"):
+            monkeypatch.setenv("PGB_CHUNK_MB", chunk_mb)
+            for var in (rng.permutation(m).astype(np.uint32), np.arange(m - 1, -1, -3, dtype=np.uint32),
+                        rng.choice(m, size=40, replace=False).astype(np.uint32)):
+                pre, blob, off = random_prefixes(rng, len(var), 0, 50)
+                sam = np.sort(rng.choice(n, size=200, replace=False)).astype(np.uint32)
+                for sel in (None, sam):
+                    got = pgb.export_to_bytes(f, var, sel, blob, off)
+                    assert got == onp.format_body(recs, var, np.arange(n) if sel is None else sel, pre)
