@@ -504,3 +504,16 @@ def test_variant_order_is_the_callers(pgb, monkeypatch):
                 for sel in (None, sam):
                     got = pgb.export_to_bytes(f, var, sel, blob, off)
                     assert got == onp.format_body(recs, var, np.arange(n) if sel is None else sel, pre)
+
+
+def test_prefix_longer_than_a_tile(pgb):
+    """A .pvar row of tens of kilobytes (a huge INFO field): the prefix spans several tiles."""
+    rng = np.random.default_rng(66)
+    n, m = 301, 6
+    recs = rng.integers(0, 256, size=(m, synth.record_size(n)), dtype=np.uint8)
+    pre, blob, off = random_prefixes(rng, m, 9000, 40000)
+    sam = np.sort(rng.choice(n, size=77, replace=False)).astype(np.uint32)
+    with pgb.PgenFile(image=image_of(recs, n)) as f:
+        for sel in (None, sam):
+            got = pgb.export_to_bytes(f, None, sel, blob, off)
+            assert got == onp.format_body(recs, np.arange(m), np.arange(n) if sel is None else sel, pre)

@@ -77,3 +77,12 @@ def test_wide_lines_span_tiles(k2sim, n):
     for variant in (0, 0x1010, 0x2000, 0x1000):
         run_sim(k2sim, rng, n, 3, None, None, (10, 60), int(rng.integers(0, 512)), variant)
         run_sim(k2sim, rng, n, 3, n // 2, 2, (10, 60), int(rng.integers(0, 512)), variant)
+
+
+def test_prefix_longer_than_a_tile(k2sim):
+    """Prefixes of tens of kilobytes: the prefix itself spans several 4-16 KiB tiles and the GT text
+    starts in a later tile than the line."""
+    rng = np.random.default_rng(6)
+    for variant in (0x1000, 0x0, 0x1010):
+        run_sim(k2sim, rng, 301, 3, None, None, (9000, 40000), int(rng.integers(0, 512)), variant)
+        run_sim(k2sim, rng, 2504, 2, 500, None, (17000, 20000), int(rng.integers(0, 512)), variant)
