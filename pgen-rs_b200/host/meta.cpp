@@ -38,7 +38,9 @@ MetaTable::MetaTable(const std::string &path) : path_(path) {
 }
 
 unsigned MetaTable::worker_threads(size_t bytes) {
-    if (bytes < (8u << 20)) return 1;
+    size_t min_bytes = 8u << 20; // below this the threads cost more than they save
+    if (const char *e = getenv("PGB_HOST_PAR_MIN_BYTES")) min_bytes = (size_t)strtoull(e, nullptr, 0);
+    if (bytes < min_bytes) return 1;
     unsigned hw = std::thread::hardware_concurrency();
     if (const char *e = getenv("PGB_HOST_THREADS")) hw = (unsigned)atoi(e);
     return std::max(1u, std::min(hw, 32u));

@@ -6,6 +6,7 @@
 #include <string.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <memory>
 #include <thread>
 
@@ -73,7 +74,7 @@ std::vector<uint32_t> filter_metadata(MetaTable &table, const std::optional<std:
         // The reference re-parses the expression for every row (pfile.rs:328), so a bad
         // expression only surfaces when there is at least one row.
         if (n == 0) return kept;
-        const unsigned T = n < 65536 ? 1u : MetaTable::worker_threads(table.data().size());
+        const unsigned T = std::min<size_t>(n, MetaTable::worker_threads(table.data().size()));
         std::vector<std::vector<uint32_t>> part(T);
         std::vector<std::string> err(T);
         std::vector<size_t> err_row(T, SIZE_MAX);
@@ -186,7 +187,7 @@ VcfPlan Pfile::plan_vcf(const std::optional<std::string> &sam_query, const std::
         plan.prefix_off[nv] = total;
         plan.prefix_blob.resize(total);
         uint8_t *base = plan.prefix_blob.data();
-        const unsigned T = total < (8u << 20) ? 1u : MetaTable::worker_threads(total);
+        const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(nv, MetaTable::worker_threads(total)));
         auto fill = [&](unsigned t) {
             const size_t a = nv / T * t, b = t + 1 == T ? nv : nv / T * (t + 1);
             for (size_t k = a; k < b; k++) {

@@ -242,3 +242,41 @@ def test_pgen10_index(pgb, tmp_path, m, type_bits, len_bytes):
     with pytest.raises(pgb.PgbError) as ei:
         pgb.pgen10_index(str(p2))
     assert ei.value.status == pgb.E_MODE
+
+
+def test_parallel_planning_equals_serial(pgb, tmp_path, monkeypatch):
+    """The .pvar/.psam parser, the predicate filter and the prefix builder split large tables over
+    worker threads at line boundaries; forced onto small random tables (mixed \\n / \\r\\n terminators,
+    empty lines, empty fields) the result must equal the serial one and the numpy oracle's."""
+    import synth
+    rng = np.random.default_rng(8)
+    for trial in range(12):
+        n_rows = int(rng.integers(1, 400))
+        n_cols = int(rng.integers(1, 7))
+        cols = ["ID"] + ["C%d" % i for i in range(1, n_cols)]
+        term = [b"\n", b"\r\n"][trial % 2]
+        lines = [b"##meta=1" + term, ("#" + "\t".join(cols)).encode() + term]
+        for r in range(n_rows):
+            fields = ["" if rng.integers(0, 9) == 0 else "".join(chr(rng.integers(65, 91)) for _ in range(rng.integers(1, 12)))
+                      for _ in range(n_cols)]
+            fields[0] = "v%d" % (r % 7)
+            lines.append("\t".join(fields).encode() + term)
+            if rng.integers(0, 10) == 0:
+                lines.append(term)  # empty line: skipped by csv
+        prefix = str(tmp_path / ("t%d" % trial))
+        open(prefix + ".pvar", "wb").write(b"".join(lines))
+        open(prefix + ".psam", "wb").write(b"#IID\tSEX\ns1\t1\ns2\t2\n")
+        open(prefix + ".pgen", "wb").write(synth.pgen_header(n_rows, 2) + bytes(n_rows))
+        q = 'ID == "v3" || ID == "v5"' if trial % 3 else None
+        plans = []
+        for par_min, threads in (("1000000000", "1"), ("0", "5"), ("0", "3")):
+            monkeypatch.setenv("PGB_HOST_PAR_MIN_BYTES", par_min)
+            monkeypatch.setenv("PGB_HOST_THREADS", threads)
+            plans.append(pgb.VcfPlan(prefix, None, q))
+        for p in plans[1:]:
+            assert (p.var_idx == plans[0].var_idx).all() and p.header == plans[0].header
+            assert (p.prefix_off == plans[0].prefix_off).all() and (p.prefix_blob == plans[0].prefix_blob).all()
+        vh, vrows = onp.parse_table(b"".join(lines))
+        assert list(plans[0].var_idx) == onp.filter_metadata(vh, vrows, q)
+        want = b"".join(onp.line_prefix(vrows[i]) for i in plans[0].var_idx)
+        assert plans[0].prefix_blob.tobytes() == want
