@@ -76,6 +76,12 @@ int pgb_open(const char *pgen_path, pgb_file **out);
  * borrowed, not copied; if it is page-locked (cudaHostAlloc/cudaHostRegister) it is
  * DMA'd from directly. */
 int pgb_open_mem(const void *pgen_image, uint64_t image_bytes, pgb_file **out);
+/* EXTENSION beyond the reference (whose Pfile asserts storage mode 0x02): opens a standard-format
+ * .pgen (storage mode 0x10).  The header walk of src/pgen.rs:18-258 (pgb_pgen10_index) becomes the
+ * record index that K1 turns into the device-side record index; the export functions then accept
+ * the variants stored as plain 2-bit hardcall records (record type 0, ceil(2N/8) bytes) and fail
+ * with PGB_E_MODE for a kept variant stored in any compressed form. */
+int pgb_open_standard(const char *pgen_path, pgb_file **out);
 void pgb_dims(const pgb_file *f, uint32_t *n_variants, uint32_t *n_samples, uint32_t *record_bytes);
 void pgb_close(pgb_file *f);
 
@@ -193,6 +199,11 @@ uint64_t pgb_dev_index_scratch_bytes(uint64_t n_lines);
  *   pitch     : bytes between consecutive records in `records` (>= record_bytes). */
 int pgb_dev_index_lines(const uint32_t *var_row, const uint64_t *prefix_off, uint64_t prefix_base, uint64_t n_lines,
                         uint32_t n_kept, uint64_t pitch, pgb_line_meta *meta, void *scratch, void *stream);
+
+/* K1 with an explicit record index: rec_off[i] = byte offset of line i's record from `records`
+ * (what the standard-format header walk yields, src/pgen.rs:100-258) instead of row * pitch. */
+int pgb_dev_index_lines_off(const uint64_t *rec_off, const uint64_t *prefix_off, uint64_t prefix_base, uint64_t n_lines,
+                            uint32_t n_kept, pgb_line_meta *meta, void *scratch, void *stream);
 
 /* K2: decode + gather + format.  kidx NULL => all n_samples samples (n_kept must equal
  * n_samples); otherwise n_kept entries (+8 padding; vectorised reads when 16-byte aligned).

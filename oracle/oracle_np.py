@@ -463,6 +463,70 @@ def load_records(pgen_path: str, faithful_u32: bool = False) -> Tuple[np.ndarray
     return raw[: m * r].reshape(m, r), m, n
 
 
+def read_pgen10(pgen_path: str):
+    """Standard-format (.pgen storage mode 0x10) header walk: what Pgen::from_file_path computes
+    (src/pgen.rs:18-137: header-format byte :50-67, block count :100-102, block-offset table
+    :104-110, main-header-body size :116-133, records offset :135-137) plus the per-variant
+    record index its check_main_header_body walks past (:172-258), with that walker's three
+    defects corrected (last block = M - 65536*b, not M % 65536; lengths are little-endian
+    integers of record_length_bytes bytes; allele-count bytes are part of the body).
+    Returns (M, N, off[M+1], typ[M], length[M]).  Test infrastructure only."""
+    data = open(pgen_path, "rb").read()
+    if data[0:2] != b"\x6c\x1b":
+        raise OracleError("bad magic")
+    if data[2] != 0x10:
+        raise OracleError("not storage mode 0x10")
+    m = int.from_bytes(data[3:7], "little")
+    n = int.from_bytes(data[7:11], "little")
+    fmt = data[11]
+    mode = fmt & 0xF
+    if mode // 4 > 1:
+        raise OracleError("unsupported record storage mode")
+    type_bits = 4 if mode // 4 == 0 else 8
+    len_bytes = mode % 4 + 1
+    ac_bytes = (fmt >> 4) & 3
+    if (fmt >> 6) & 3 != 1:
+        raise OracleError("provisional_ref_storage != 1 (pgen.rs:66)")
+    nb = (m + 65535) // 65536
+    block_off = [int.from_bytes(data[12 + 8 * b:20 + 8 * b], "little") for b in range(nb)]
+    pos = 12 + 8 * nb
+    off = np.zeros(m + 1, dtype=np.uint64)
+    typ = np.zeros(m, dtype=np.uint8)
+    length = np.zeros(m, dtype=np.uint32)
+    v = 0
+    for b in range(nb):
+        cnt = 65536 if b + 1 < nb else m - 65536 * b
+        tb = (cnt * type_bits + 7) // 8
+        tbytes = data[pos:pos + tb]
+        lbytes = data[pos + tb:pos + tb + cnt * len_bytes]
+        pos += tb + cnt * len_bytes + cnt * ac_bytes
+        o = block_off[b]
+        for k in range(cnt):
+            t = tbytes[k] if type_bits == 8 else (tbytes[k // 2] >> ((k & 1) * 4)) & 0xF
+            ln = int.from_bytes(lbytes[k * len_bytes:(k + 1) * len_bytes], "little")
+            off[v], typ[v], length[v] = o, t, ln
+            o += ln
+            v += 1
+        if b + 1 == nb:
+            off[m] = o
+    if nb == 0:
+        off[0] = pos
+    return m, n, off, typ, length
+
+
+def records_standard(pgen_path: str, rows: Sequence[int]) -> np.ndarray:
+    """The plain 2-bit records (type 0, ceil(2N/8) bytes) of the given variants of a mode-0x10 file."""
+    m, n, off, typ, length = read_pgen10(pgen_path)
+    r = record_size(n)
+    data = np.fromfile(pgen_path, dtype=np.uint8)
+    out = np.zeros((len(rows), r), dtype=np.uint8)
+    for i, v in enumerate(rows):
+        if typ[v] != 0 or length[v] != r:
+            raise OracleError("variant %d is not a plain 2-bit record" % v)
+        out[i] = data[int(off[v]):int(off[v]) + r]
+    return out
+
+
 def output_vcf(prefix: str, sam_query: Optional[str], var_query: Optional[str], out_path: str,
                var_idx: Optional[Sequence[int]] = None, sam_idx: Optional[Sequence[int]] = None) -> None:
     """Pfile::output_vcf, pfile.rs:104-194.  Selections come from the queries unless explicit

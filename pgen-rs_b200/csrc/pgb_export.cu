@@ -92,7 +92,15 @@ struct pgb_file {
     bool image_pinned = false;
     uint64_t bytes = 0; // file or image size
     uint32_t M = 0, N = 0, R = 0;
+    // standard-format (.pgen storage mode 0x10) handles: the per-variant record index from the
+    // header walk (pgb_pgen10_index, src/pgen.rs:100-258); empty for fixed-width mode 0x02 files
+    bool standard = false;
+    std::vector<uint64_t> off10;
+    std::vector<uint8_t> type10;
+    std::vector<uint32_t> len10;
     std::mutex mu; // one export at a time per handle
+    // file offset of variant v's record: pfile.rs:165 in u64, or the mode-0x10 index
+    uint64_t rec_off(uint64_t v) const { return standard ? off10[v] : pgb_record_offset(v, R); }
 };
 
 namespace {
@@ -193,9 +201,9 @@ struct Chunk {
     uint64_t a, b;       // line range [a, b)
     uint64_t out_off;    // offset of the chunk in the body
     uint64_t out_bytes;
-    uint64_t v0, v1;     // covering file rows [v0, v1]
-    bool dense;          // true: stage the covering row range; false: stage kept rows compactly
-    uint64_t in_rows;    // rows staged
+    uint64_t o0;         // file offset of the first staged record byte (dense)
+    bool dense;          // true: stage the covering byte range; false: stage kept rows compactly
+    uint64_t in_bytes;   // record bytes staged
     uint32_t max_pfx;
 };
 
@@ -406,13 +414,14 @@ struct Stage {
 
 Stage stage_layout(const Job &j, const Chunk &c, bool records_inline) {
     Stage s;
-    s.rec_bytes = records_inline ? c.in_rows * (uint64_t)j.f->R : 0;
+    s.rec_bytes = records_inline ? c.in_bytes : 0;
     uint64_t n = c.b - c.a;
     s.pfx_pos = align_up(s.rec_bytes + 16, kAlign);
     s.pfx_bytes = j.prefix_off[c.b] - j.prefix_off[c.a];
     s.off_pos = align_up(s.pfx_pos + s.pfx_bytes, kAlign);
     s.row_pos = align_up(s.off_pos + (n + 1) * 8, kAlign);
-    s.total = align_up(s.row_pos + (c.dense ? n * 4 : 0), kAlign);
+    // per-line record index input of K1: u32 row numbers (fixed-width) or u64 byte offsets (standard format)
+    s.total = align_up(s.row_pos + (c.dense ? n * (j.f->standard ? 8 : 4) : 0), kAlign);
     return s;
 }
 
@@ -547,7 +556,7 @@ int run_device_inner(Job *job, DeviceWork *w, std::deque<Pending> &q, std::mutex
         const bool rec_direct = f->image && f->image_pinned && ch.dense; // DMA records straight from the image
         const Stage lay = stage_layout(*job, ch, !rec_direct);
         const uint64_t n = ch.b - ch.a;
-        const uint64_t rec_dev_bytes = ch.in_rows * (uint64_t)R;
+        const uint64_t rec_dev_bytes = ch.in_bytes;
         const uint64_t d_rec_region = rec_direct ? align_up(rec_dev_bytes + 16, kAlign) : 0;
         rc = ensure_slot(s, lay.total + d_rec_region, ch.out_bytes + 64, n, need_h_out);
         if (rc) return rc;
@@ -556,12 +565,12 @@ int run_device_inner(Job *job, DeviceWork *w, std::deque<Pending> &q, std::mutex
         uint8_t *h = s.h_in;
         if (!rec_direct) {
             if (ch.dense) {
-                const uint64_t off = pgb_record_offset(ch.v0, R);
+                const uint64_t off = ch.o0;
                 if (f->image) memcpy(h, f->image + off, rec_dev_bytes);
                 else if ((rc = read_fully(f->fd, h, rec_dev_bytes, off))) return rc;
             } else {
                 for (uint64_t i = 0; i < n; i++) {
-                    const uint64_t off = pgb_record_offset(job->var_idx[ch.a + i], R);
+                    const uint64_t off = f->rec_off(job->var_idx ? job->var_idx[ch.a + i] : ch.a + i);
                     if (f->image) memcpy(h + i * R, f->image + off, R);
                     else if ((rc = read_fully(f->fd, h + i * R, R, off))) return rc;
                 }
@@ -570,10 +579,14 @@ int run_device_inner(Job *job, DeviceWork *w, std::deque<Pending> &q, std::mutex
         }
         memcpy(h + lay.pfx_pos, job->prefix_blob + job->prefix_off[ch.a], lay.pfx_bytes);
         memcpy(h + lay.off_pos, job->prefix_off + ch.a, (n + 1) * 8);
-        if (ch.dense) {
+        if (ch.dense && f->standard) {
+            uint64_t *ro = (uint64_t *)(h + lay.row_pos);
+            for (uint64_t i = 0; i < n; i++) ro[i] = f->rec_off(job->var_idx ? job->var_idx[ch.a + i] : ch.a + i) - ch.o0;
+        } else if (ch.dense) {
             uint32_t *vr = (uint32_t *)(h + lay.row_pos);
-            if (job->var_idx) for (uint64_t i = 0; i < n; i++) vr[i] = (uint32_t)(job->var_idx[ch.a + i] - ch.v0);
-            else for (uint64_t i = 0; i < n; i++) vr[i] = (uint32_t)i;
+            const uint64_t v0 = (ch.o0 - 12) / (R ? R : 1);
+            if (job->var_idx) for (uint64_t i = 0; i < n; i++) vr[i] = (uint32_t)(job->var_idx[ch.a + i] - v0);
+            else for (uint64_t i = 0; i < n; i++) vr[i] = (uint32_t)(ch.a + i - v0);
         }
 
         job->lap("staged", ci);
@@ -582,7 +595,7 @@ int run_device_inner(Job *job, DeviceWork *w, std::deque<Pending> &q, std::mutex
         uint8_t *d_stage = s.d_in + d_rec_region;
         const uint8_t *d_records;
         if (rec_direct) {
-            CU(cudaMemcpyAsync(s.d_in, f->image + pgb_record_offset(ch.v0, R), rec_dev_bytes, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(s.d_in, f->image + ch.o0, rec_dev_bytes, cudaMemcpyHostToDevice, st));
             CU(cudaMemsetAsync(s.d_in + rec_dev_bytes, 0, 16, st));
             d_records = s.d_in;
             w->h2d += rec_dev_bytes;
@@ -592,9 +605,13 @@ int run_device_inner(Job *job, DeviceWork *w, std::deque<Pending> &q, std::mutex
         CU(cudaMemcpyAsync(d_stage, h, lay.total, cudaMemcpyHostToDevice, st));
         w->h2d += lay.total;
         CU(cudaEventRecord(s.ev_k0, st));
-        rc = pgb_dev_index_lines(ch.dense ? (const uint32_t *)(d_stage + lay.row_pos) : nullptr,
-                                 (const uint64_t *)(d_stage + lay.off_pos), job->prefix_off[ch.a], n, (uint32_t)K, R,
-                                 s.d_meta, s.d_scratch, st);
+        if (ch.dense && f->standard)
+            rc = pgb_dev_index_lines_off((const uint64_t *)(d_stage + lay.row_pos), (const uint64_t *)(d_stage + lay.off_pos),
+                                         job->prefix_off[ch.a], n, (uint32_t)K, s.d_meta, s.d_scratch, st);
+        else
+            rc = pgb_dev_index_lines(ch.dense ? (const uint32_t *)(d_stage + lay.row_pos) : nullptr,
+                                     (const uint64_t *)(d_stage + lay.off_pos), job->prefix_off[ch.a], n, (uint32_t)K, R,
+                                     s.d_meta, s.d_scratch, st);
         if (rc) return rc;
         rc = pgb_dev_format_lines(d_records, s.d_meta, n, d_stage + lay.pfx_pos, gather ? c->d_kidx : nullptr, (uint32_t)K,
                                   ch.max_pfx, s.d_out, job->variant, st);
@@ -681,7 +698,16 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
     uint64_t total_pfx = 0;
     for (uint64_t i = 0; i < n_var; i++) {
         const uint64_t v = var_idx ? var_idx[i] : i;
-        if (pgb_record_offset(v, R) + R > f->bytes) {
+        if (v >= f->M && f->standard) {
+            pgb_set_error("variant row %llu outside the %u variants of the file", (unsigned long long)v, f->M);
+            return PGB_E_RANGE;
+        }
+        if (f->standard && (f->type10[v] != 0 || f->len10[v] != R)) {
+            pgb_set_error("variant row %llu is stored as record type %u, length %u: only plain 2-bit hardcall records "
+                          "(type 0, %u bytes) can be decoded", (unsigned long long)v, f->type10[v], f->len10[v], R);
+            return PGB_E_MODE;
+        }
+        if (f->rec_off(v) + R > f->bytes) {
             pgb_set_error("variant row %llu lies outside the .pgen (read_exact, pfile.rs:170)", (unsigned long long)v);
             return PGB_E_RANGE;
         }
@@ -743,29 +769,28 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
         while (line < end) {
             Chunk c;
             c.a = line;
-            c.v0 = var_idx ? var_idx[line] : line;
             uint64_t b = line + 1;
-            uint64_t vmin = c.v0, vmax = c.v0;
+            uint64_t omin = f->rec_off(var_idx ? var_idx[line] : line), omax = omin;
             uint32_t maxp = (uint32_t)(prefix_off[line + 1] - prefix_off[line]);
             while (b < end) {
                 const uint64_t ob = out_before(b + 1) - out_before(line);
                 if (ob > chunk_out) break;
-                const uint64_t v = var_idx ? var_idx[b] : b;
-                const uint64_t nmin = std::min(vmin, v), nmax = std::max(vmax, v);
+                const uint64_t o = f->rec_off(var_idx ? var_idx[b] : b);
+                const uint64_t nmin = std::min(omin, o), nmax = std::max(omax, o);
                 const uint64_t compact = (b + 1 - line) * (uint64_t)R; // bytes of the kept rows alone
                 if (compact > chunk_in) break;
-                if ((nmax - nmin) >= 0xffffffffull) break;
-                vmin = nmin; vmax = nmax;
+                if (!f->standard && (nmax - nmin) / (R ? R : 1) >= 0xffffffffull) break;
+                omin = nmin; omax = nmax;
                 maxp = std::max(maxp, (uint32_t)(prefix_off[b + 1] - prefix_off[b]));
                 b++;
             }
             c.b = b;
-            c.v0 = vmin; c.v1 = vmax;
-            const uint64_t cover_rows = vmax - vmin + 1, kept_rows = b - line;
-            // density >= 25 %: move the whole covering row range with one DMA (at most 4 x chunk_in bytes,
+            c.o0 = omin;
+            const uint64_t cover_bytes = omax - omin + R, kept_bytes = (b - line) * (uint64_t)R;
+            // density >= 25 %: move the whole covering byte range with one DMA (at most 4 x chunk_in bytes,
             // free on the otherwise idle H2D direction) instead of gathering the kept rows on the CPU
-            c.dense = cover_rows <= 4 * kept_rows;
-            c.in_rows = c.dense ? cover_rows : kept_rows;
+            c.dense = cover_bytes <= 4 * kept_bytes;
+            c.in_bytes = c.dense ? cover_bytes : kept_bytes;
             c.out_off = out_before(line);
             c.out_bytes = out_before(b) - c.out_off;
             c.max_pfx = maxp;
@@ -909,6 +934,33 @@ extern "C" int pgb_open(const char *pgen_path, pgb_file **out) {
     pgb_file *f = new pgb_file();
     int rc = parse_header(h, got, f);
     if (rc) { close(fd); delete f; return rc; }
+    struct stat st;
+    if (fstat(fd, &st) != 0) { pgb_set_error("fstat: %s", strerror(errno)); close(fd); delete f; return PGB_E_IO; }
+    f->fd = fd;
+    f->bytes = (uint64_t)st.st_size;
+    *out = f;
+    return PGB_OK;
+}
+
+extern "C" int pgb_open_standard(const char *pgen_path, pgb_file **out) {
+    pgb_clear_error();
+    if (!pgen_path || !out) return PGB_E_ARG;
+    *out = nullptr;
+    pgb_pgen10_info info;
+    int rc = pgb_pgen10_index(pgen_path, &info, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    pgb_file *f = new pgb_file();
+    f->standard = true;
+    f->M = info.n_variants;
+    f->N = info.n_samples;
+    f->R = pgb_record_bytes(f->N);
+    f->off10.resize((size_t)f->M + 1);
+    f->type10.resize(std::max<size_t>(f->M, 1));
+    f->len10.resize(std::max<size_t>(f->M, 1));
+    rc = pgb_pgen10_index(pgen_path, &info, f->off10.data(), f->type10.data(), f->len10.data());
+    if (rc) { delete f; return rc; }
+    const int fd = open(pgen_path, O_RDONLY);
+    if (fd < 0) { pgb_set_error("open %s: %s", pgen_path, strerror(errno)); delete f; return PGB_E_IO; }
     struct stat st;
     if (fstat(fd, &st) != 0) { pgb_set_error("fstat: %s", strerror(errno)); close(fd); delete f; return PGB_E_IO; }
     f->fd = fd;

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(1024) k1_scan(uint64_t *__restrict__ tile_sum,
 }
 
 __global__ void __launch_bounds__(K1_THREADS) k1_emit(const uint32_t *__restrict__ var_row,
+                                                      const uint64_t *__restrict__ rec_off_in,
                                                       const uint64_t *__restrict__ prefix_off, uint64_t prefix_base,
                                                       uint64_t n, uint64_t fixed, uint64_t pitch,
                                                       const uint64_t *__restrict__ tile_base,
@@ -171,7 +172,9 @@ __global__ void __launch_bounds__(K1_THREADS) k1_emit(const uint32_t *__restrict
             const uint64_t row = var_row ? (uint64_t)var_row[i] : i;
             uint4 a, b;
             a.x = (uint32_t)off; a.y = (uint32_t)(off >> 32);
-            const uint64_t ro = row * pitch;
+            // device record index: explicit offsets (standard-format .pgen, from the header walk of
+            // pgen.rs:100-258) or row * pitch (fixed-width mode 0x02, pfile.rs:165)
+            const uint64_t ro = rec_off_in ? rec_off_in[i] : row * pitch;
             a.z = (uint32_t)ro; a.w = (uint32_t)(ro >> 32);
             const uint64_t pf = po[k] - prefix_base;
             b.x = (uint32_t)pf; b.y = (uint32_t)(pf >> 32);
@@ -379,9 +382,9 @@ extern "C" uint64_t pgb_dev_index_scratch_bytes(uint64_t n_lines) {
     return (tiles + 1) * sizeof(uint64_t);
 }
 
-extern "C" int pgb_dev_index_lines(const uint32_t *var_row, const uint64_t *prefix_off, uint64_t prefix_base,
-                                   uint64_t n_lines, uint32_t n_kept, uint64_t pitch, pgb_line_meta *meta,
-                                   void *scratch, void *stream) {
+static int index_lines_impl(const uint32_t *var_row, const uint64_t *rec_off_in, const uint64_t *prefix_off,
+                            uint64_t prefix_base, uint64_t n_lines, uint32_t n_kept, uint64_t pitch, pgb_line_meta *meta,
+                            void *scratch, void *stream) {
     if (!prefix_off || !meta || !scratch) return PGB_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const uint64_t fixed = 4ull * n_kept + 1ull;
@@ -397,11 +400,24 @@ extern "C" int pgb_dev_index_lines(const uint32_t *var_row, const uint64_t *pref
     int rc = check_launch("k1_scan");
     if (rc) return rc;
     if (tiles) {
-        k1_emit<<<(unsigned)tiles, K1_THREADS, 0, st>>>(var_row, prefix_off, prefix_base, n_lines, fixed, pitch, tile_sum,
-                                                       meta);
+        k1_emit<<<(unsigned)tiles, K1_THREADS, 0, st>>>(var_row, rec_off_in, prefix_off, prefix_base, n_lines, fixed, pitch,
+                                                       tile_sum, meta);
         rc = check_launch("k1_emit");
     }
     return rc;
+}
+
+extern "C" int pgb_dev_index_lines(const uint32_t *var_row, const uint64_t *prefix_off, uint64_t prefix_base,
+                                   uint64_t n_lines, uint32_t n_kept, uint64_t pitch, pgb_line_meta *meta,
+                                   void *scratch, void *stream) {
+    return index_lines_impl(var_row, nullptr, prefix_off, prefix_base, n_lines, n_kept, pitch, meta, scratch, stream);
+}
+
+extern "C" int pgb_dev_index_lines_off(const uint64_t *rec_off, const uint64_t *prefix_off, uint64_t prefix_base,
+                                       uint64_t n_lines, uint32_t n_kept, pgb_line_meta *meta, void *scratch,
+                                       void *stream) {
+    if (!rec_off) return PGB_E_ARG;
+    return index_lines_impl(nullptr, rec_off, prefix_off, prefix_base, n_lines, n_kept, 0, meta, scratch, stream);
 }
 
 template <bool GATHER, int HINT, int REPL, int IPW, bool ONE>

@@ -70,6 +70,7 @@ _vp, _u64, _u32, _i = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
 SYMBOLS = {
     "pgb_open": (_i, [C.c_char_p, C.POINTER(_vp)]),
     "pgb_open_mem": (_i, [_vp, _u64, C.POINTER(_vp)]),
+    "pgb_open_standard": (_i, [C.c_char_p, C.POINTER(_vp)]),
     "pgb_dims": (None, [_vp, C.POINTER(_u32), C.POINTER(_u32), C.POINTER(_u32)]),
     "pgb_close": (None, [_vp]),
     "pgb_record_bytes": (_u32, [_u32]),
@@ -95,6 +96,7 @@ SYMBOLS = {
     "pgb_dev_compact_samples": (_i, [_vp, _u32, _vp, _vp, _vp]),
     "pgb_dev_index_scratch_bytes": (_u64, [_u64]),
     "pgb_dev_index_lines": (_i, [_vp, _vp, _u64, _u64, _u32, _u64, _vp, _vp, _vp]),
+    "pgb_dev_index_lines_off": (_i, [_vp, _vp, _u64, _u64, _u32, _vp, _vp, _vp]),
     "pgb_dev_format_lines": (_i, [_vp, _vp, _u64, _vp, _vp, _u32, _u32, _vp, _i, _vp]),
     "pgb_dev_synth_records": (_i, [_vp, _u64, _u64, _u64, _u64, _u32, _vp]),
     "pgb_dev_fill": (_i, [_vp, _u64, _i, _vp]),
@@ -137,10 +139,12 @@ class PgenFile:
     """Handle returned by pgb_open / pgb_open_mem."""
 
     def __init__(self, path: Optional[str] = None, image: Optional[np.ndarray] = None, image_ptr: int = 0,
-                 image_bytes: int = 0):
+                 image_bytes: int = 0, standard: bool = False):
         h = _vp()
         self._keep = None
-        if path is not None:
+        if path is not None and standard:
+            _check(lib.pgb_open_standard(os.fsencode(path), C.byref(h)), f"pgb_open_standard({path})")
+        elif path is not None:
             _check(lib.pgb_open(os.fsencode(path), C.byref(h)), f"pgb_open({path})")
         elif image is not None:
             self._keep = image

@@ -517,3 +517,61 @@ def test_prefix_longer_than_a_tile(pgb):
         for sel in (None, sam):
             got = pgb.export_to_bytes(f, None, sel, blob, off)
             assert got == onp.format_body(recs, np.arange(m), np.arange(n) if sel is None else sel, pre)
+
+
+def _write_standard_pgen(path, n, types, lens, payload, type_bits=8, len_bytes=2):
+    """A mode-0x10 .pgen: header-format byte, block-offset table, per-block record types and
+    lengths (the layout src/pgen.rs:100-258 walks), then the records."""
+    m = len(types)
+    nb = (m + 65535) // 65536
+    mode = (0 if type_bits == 4 else 4) + (len_bytes - 1)
+    hdr = b"\x6c\x1b\x10" + m.to_bytes(4, "little") + n.to_bytes(4, "little") + bytes([mode | 0x40])
+    body = b""
+    for b in range(nb):
+        a, e = b * 65536, min(m, (b + 1) * 65536)
+        t = [int(x) for x in types[a:e]]
+        if type_bits == 4:
+            t = t + [0] * (len(t) % 2)
+            body += bytes(t[i] | (t[i + 1] << 4) for i in range(0, len(t), 2))
+        else:
+            body += bytes(t)
+        body += b"".join(int(x).to_bytes(len_bytes, "little") for x in lens[a:e])
+    rec0 = 12 + 8 * nb + len(body)
+    cum = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    offs = [rec0 + int(cum[b * 65536]) for b in range(nb)]
+    with open(path, "wb") as f:
+        f.write(hdr + b"".join(o.to_bytes(8, "little") for o in offs) + body + payload)
+
+
+def test_standard_format_record_index(pgb, tmp_path):
+    """EXTENSION: a mode-0x10 .pgen (two variant blocks) whose records are a mix of plain 2-bit
+    records and compressed ones of random lengths.  The header walk feeds the device record index;
+    kept plain records export bit-exactly (dense range DMA and compact staging), a kept compressed
+    record is PGB_E_MODE, and pgb_open keeps rejecting the file like the reference (pfile.rs:53)."""
+    rng = np.random.default_rng(100)
+    n, m = 37, 65536 + 1500
+    r = synth.record_size(n)
+    plain = rng.random(m) < 0.8
+    types = np.where(plain, 0, rng.integers(1, 8, size=m)).astype(np.uint8)
+    lens = np.where(plain, r, rng.integers(1, 40, size=m)).astype(np.int64)
+    payload = rng.integers(0, 256, size=int(lens.sum()) + 64, dtype=np.uint8).tobytes()
+    path = str(tmp_path / "std.pgen")
+    _write_standard_pgen(path, n, types, lens, payload)
+    with pytest.raises(pgb.PgbError) as ei:
+        pgb.PgenFile(path)
+    assert ei.value.status == pgb.E_MODE
+    plain_rows = np.nonzero(plain)[0].astype(np.uint32)
+    sam = np.sort(rng.choice(n, size=11, replace=False)).astype(np.uint32)
+    with pgb.PgenFile(path, standard=True) as f:
+        assert (f.n_variants, f.n_samples, f.record_bytes) == (m, n, r)
+        for rows in (plain_rows, plain_rows[::7], plain_rows[[3, 65000 % len(plain_rows), len(plain_rows) - 1]]):
+            recs = onp.records_standard(path, rows)
+            pre, blob, off = random_prefixes(rng, len(rows), 0, 30)
+            for sel in (None, sam):
+                got = pgb.export_to_bytes(f, rows, sel, blob, off)
+                assert got == onp.format_body(recs, np.arange(len(rows)), np.arange(n) if sel is None else sel, pre)
+        bad = np.array([plain_rows[0], np.nonzero(~plain)[0][0]], dtype=np.uint32)
+        pre, blob, off = random_prefixes(rng, 2, 1, 5)
+        with pytest.raises(pgb.PgbError) as ei:
+            pgb.export_to_bytes(f, bad, None, blob, off)
+        assert ei.value.status == pgb.E_MODE
