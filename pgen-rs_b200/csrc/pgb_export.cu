@@ -756,7 +756,10 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
 
     lap("ctx leased");
     // ---- plan: contiguous line ranges per device balanced by output bytes, then chunks ----
-    const uint64_t chunk_out = env_u64("PGB_CHUNK_MB", 128) << 20; // 64..1024 MB measured within 3 % of each other
+    // Output bytes per chunk: 128 MiB for big exports (64..1024 MiB measured within 3 % of each other),
+    // smaller for small ones so that at least ~16 chunks keep H2D, kernels, D2H and the sink overlapped
+    uint64_t chunk_out = env_u64("PGB_CHUNK_MB", 128) << 20;
+    if (!getenv("PGB_CHUNK_MB")) chunk_out = std::min<uint64_t>(128ull << 20, std::max<uint64_t>(8ull << 20, total / 16));
     const uint64_t chunk_in = env_u64("PGB_CHUNK_IN_MB", 128) << 20;
     auto out_before = [&](uint64_t i) { return (prefix_off[i] - prefix_off[0]) + i * fixed; };
     uint64_t seq = 0;
