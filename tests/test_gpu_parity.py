@@ -575,3 +575,27 @@ def test_standard_format_record_index(pgb, tmp_path):
         with pytest.raises(pgb.PgbError) as ei:
             pgb.export_to_bytes(f, bad, None, blob, off)
         assert ei.value.status == pgb.E_MODE
+
+
+def test_logical_shards_on_one_gpu_concatenate(pgb):
+    """The multi-GPU partition exercised with one physical GPU ("fake cluster"): the
+    contiguous ranges of pgb_shard_plan exported one after the other must concatenate to the single
+    export, and each shard's size must equal the planned byte range."""
+    rng = np.random.default_rng(91)
+    n, m = 911, 5000
+    recs = synth.synth_records(9, 0, m, n)
+    var = np.sort(rng.choice(m, size=3500, replace=False)).astype(np.uint32)
+    sam = np.sort(rng.choice(n, size=300, replace=False)).astype(np.uint32)
+    pre, blob, off = random_prefixes(rng, len(var), 0, 120)
+    with pgb.PgenFile(image=image_of(recs, n)) as f:
+        whole = pgb.export_to_bytes(f, var, sam, blob, off)
+        assert whole == onp.format_body(recs, var, sam, pre)
+        for shards in (2, 4, 8):
+            lb, bb = pgb.shard_plan(len(sam), off, shards)
+            parts = []
+            for g in range(shards):
+                a, b = int(lb[g]), int(lb[g + 1])
+                sub_off = off[a:b + 1]
+                parts.append(pgb.export_to_bytes(f, var[a:b], sam, blob, sub_off) if b > a else b"")
+                assert len(parts[-1]) == int(bb[g + 1] - bb[g])
+            assert b"".join(parts) == whole
