@@ -861,6 +861,8 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
         for (auto &t : th) t.join();
     }
     lap("devices done");
+    sink->pool = nullptr; // both die with this call
+    sink->map = nullptr;
     int rc = job.status.load();
     if (rc != PGB_OK) {
         pgb_set_error("%s", job.err);
