@@ -58,6 +58,8 @@ WORKLOADS = {
                   desc="configs[2]: synthetic 1000G chr22 shape, 2504 samples x 1.1M variants, keep all"),
     "chr22-wide-prefix": dict(n=2504, m=1_100_000, k=None, mk=None, width=163, seed=3,
                               desc="configs[2] shape with 163-byte line prefixes (the mean of the real 1000G basic1.pvar)"),
+    "random1": dict(n=300, m=200_000, k=None, mk=None, width=40, seed=2,
+                    desc="configs[1] shape: 300 samples x 200000 variants, keep all (short 1.2 KB lines)"),
     "gather": dict(n=2504, m=1_100_000, k=250, mk=550_000, width=40, seed=3,
                    desc="configs[3]: chr22 shape, 10% samples (250) x 50% variants (550000)"),
     "biobank-block": dict(n=500_000, m=8192, k=None, mk=None, width=40, seed=5,

@@ -442,7 +442,6 @@ static int launch_k2(const pgb_k2_params &p, cudaStream_t st) {
 
 template <bool GATHER, int HINT, int REPL>
 static int launch_k2_ipw(const pgb_k2_params &p, cudaStream_t st, int ipw) {
-    if (ipw == 0) ipw = GATHER ? 4 : 1; // measured best on the chr22 shapes (profiles/README.md)
     switch (ipw) {
     case 1: return launch_k2<GATHER, HINT, REPL, 1>(p, st);
     case 2: return launch_k2<GATHER, HINT, REPL, 2>(p, st);
@@ -452,9 +451,8 @@ static int launch_k2_ipw(const pgb_k2_params &p, cudaStream_t st, int ipw) {
 }
 
 // variant: bits 0-3  store hint (0 => .cs streaming, the measured best; 2 => default write-back)
-//          bits 4-7  LUT copies (0 => default: 8 interleaved bank-conflict-free copies for keep-all, one
-//                    copy for gather; 1 => 8 copies; 2 => one copy)
-//          bits 8-11 items per warp (0 => 1 keep-all / 4 gather; 1, 2, 4, 8)
+//          bits 4-7  LUT copies (0 => default, see below; 1 => 8 interleaved bank-conflict-free copies; 2 => one)
+//          bits 8-11 items per warp (0 => default; 1, 2, 4, 8)
 //          bits 12-15 tile size = 4 KiB << n (0 => 16 KiB)
 extern "C" int pgb_dev_format_lines(const uint8_t *records, const pgb_line_meta *meta, uint64_t n_lines,
                                     const uint8_t *prefix_blob, const uint32_t *kidx, uint32_t n_kept,
@@ -471,14 +469,19 @@ extern "C" int pgb_dev_format_lines(const uint8_t *records, const pgb_line_meta 
     p.K = n_kept;
     const int hint = (variant & 0xF) == 2 ? 0 : 1;
     const int lsel = (variant >> 4) & 0xF;
-    const bool repl8 = lsel == 1 || (lsel == 0 && kidx == nullptr);
-    const int ipw = (variant >> 8) & 0xF;
+    int ipw = (variant >> 8) & 0xF;
     const int tsel = (variant >> 12) & 0xF;
     p.tile_bytes = tsel ? (4096u << tsel) : 16384u;
     const uint64_t max_line = (uint64_t)max_prefix_len + 4ull * n_kept + 1ull;
     const uint64_t nt = (max_line + 511ull + p.tile_bytes - 1) / p.tile_bytes;
     if (nt > 0x7fffffffull) return PGB_E_ARG;
     p.n_tiles = (uint32_t)nt;
+    // Defaults measured on B200 (profiles/README.md): long keep-all lines -> 8 conflict-free LUT copies and one
+    // item per warp; gather and short lines (<= 4 KiB: the 32 KB table would cost more to build than the CTA's
+    // lines to format) -> one LUT copy and four items per warp.
+    const bool light = kidx != nullptr || (nt == 1 && max_line <= 4096);
+    const bool repl8 = lsel == 1 || (lsel == 0 && !light);
+    if (ipw == 0) ipw = light ? 4 : 1;
     // bytes of a record worth prefetching: all of it for keep-all, up to the last kept sample otherwise
     p.row_bytes_hint = kidx ? 0u : (n_kept + 3u) / 4u + 1u;
     p.kidx_vec = kidx && ((uintptr_t)kidx & 15u) == 0 ? 1u : 0u;
