@@ -533,6 +533,8 @@ def main():
     ap.add_argument("--workload", default="chr22", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-file", action="store_true", help="skip the e2e leg that writes a file")
+    ap.add_argument("--n-samples", type=int, default=0, help="kernel development: override the workload's sample count")
+    ap.add_argument("--n-variants", type=int, default=0, help="kernel development: override the workload's variant count")
     ap.add_argument("--no-e2e", action="store_true", help="kernel development: device-resident part only, short line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -543,7 +545,11 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29531"), os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.n_samples:
+        wl["n"] = args.n_samples
+    if args.n_variants:
+        wl["m"] = args.n_variants
     if args.impl == "reference":
         run_reference(args, wl, rank, world)
     else:

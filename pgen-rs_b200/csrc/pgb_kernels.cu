@@ -476,12 +476,13 @@ extern "C" int pgb_dev_format_lines(const uint8_t *records, const pgb_line_meta 
     const uint64_t nt = (max_line + 511ull + p.tile_bytes - 1) / p.tile_bytes;
     if (nt > 0x7fffffffull) return PGB_E_ARG;
     p.n_tiles = (uint32_t)nt;
-    // Defaults measured on B200 (profiles/README.md): long keep-all lines -> 8 conflict-free LUT copies and one
-    // item per warp; gather and short lines (<= 4 KiB: the 32 KB table would cost more to build than the CTA's
-    // lines to format) -> one LUT copy and four items per warp.
-    const bool light = kidx != nullptr || (nt == 1 && max_line <= 4096);
-    const bool repl8 = lsel == 1 || (lsel == 0 && !light);
-    if (ipw == 0) ipw = light ? 4 : 1;
+    // Defaults measured on B200 (profiles/README.md, 2.5 GB of output per shape): lines > 7 KiB (and tiled
+    // lines) -> 8 conflict-free LUT copies, one item per warp; 3-7 KiB -> one LUT copy (the 32 KB table costs
+    // more to build than it saves), one item per warp; <= 3 KiB and gather -> one copy, four items per warp.
+    const bool gatherp = kidx != nullptr;
+    const bool small_lines = nt == 1 && max_line <= 3072, mid_lines = nt == 1 && max_line <= 7168;
+    const bool repl8 = lsel == 1 || (lsel == 0 && !gatherp && !mid_lines);
+    if (ipw == 0) ipw = (gatherp || small_lines) ? 4 : 1;
     // bytes of a record worth prefetching: all of it for keep-all, up to the last kept sample otherwise
     p.row_bytes_hint = kidx ? 0u : (n_kept + 3u) / 4u + 1u;
     p.kidx_vec = kidx && ((uintptr_t)kidx & 15u) == 0 ? 1u : 0u;
