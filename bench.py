@@ -311,9 +311,9 @@ def run_b200(args, wl, rank, world, local_rank):
                                               K, R, d_meta.data_ptr(), d_scr.data_ptr(), stream), "K1")
 
     def k2():
-        pgb200._check(lib.pgb_dev_format_lines(recs.data_ptr(), d_meta.data_ptr(), n_lines, d_blob.data_ptr(),
-                                               None if d_kidx is None else d_kidx.data_ptr(), K, width, d_out.data_ptr(),
-                                               variant, stream), "K2")
+        pgb200._check(lib.pgb_dev_format_lines_ex(recs.data_ptr(), R, d_meta.data_ptr(), n_lines, d_blob.data_ptr(), 0, 0,
+                                                  None if d_kidx is None else d_kidx.data_ptr(), K, width, d_out.data_ptr(),
+                                                  variant, stream), "K2")
 
     def barrier():
         torch.cuda.synchronize()

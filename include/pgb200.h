@@ -216,6 +216,23 @@ int pgb_dev_format_lines(const uint8_t *records, const pgb_line_meta *meta, uint
                          const uint8_t *prefix_blob, const uint32_t *kidx, uint32_t n_kept, uint32_t max_prefix_len,
                          uint8_t *out, int variant, void *stream);
 
+/* K1, general form: the record index is rec_off[i] when rec_off is non-NULL, else var_row[i] * pitch
+ * (var_row NULL => i * pitch).  The prefix of line i is prefix_len[i] bytes at prefix_off[i] when
+ * prefix_len is non-NULL (rows of a raw .pvar image: prefix_off then holds n_lines entries and need not
+ * be contiguous), else prefix_off[i+1] - prefix_off[i] bytes; suffix_len (0..4) constant bytes are
+ * appended to every prefix by K2 and counted in pgb_line_meta::pfx_len. */
+int pgb_dev_index_lines_ex(const uint32_t *var_row, const uint64_t *rec_off, uint64_t pitch, const uint64_t *prefix_off,
+                           const uint32_t *prefix_len, uint32_t suffix_len, uint64_t prefix_base, uint64_t n_lines,
+                           uint32_t n_kept, pgb_line_meta *meta, void *scratch, void *stream);
+
+/* K2, general form.  record_bytes = ceil(2 * n_samples / 8) of the file (needed to size the shared-memory
+ * staging of the batch path when kidx is non-NULL; 0 = unknown => per-line path).  `suffix`: suffix_len
+ * (0..4) bytes, little-endian, written after the prefix_blob bytes of every line — "\tGT" (0x0054 4709,
+ * length 3) turns a raw .pvar row into the line prefix of src/pfile.rs:157-161 on the device. */
+int pgb_dev_format_lines_ex(const uint8_t *records, uint32_t record_bytes, const pgb_line_meta *meta, uint64_t n_lines,
+                            const uint8_t *prefix_blob, uint32_t suffix, uint32_t suffix_len, const uint32_t *kidx,
+                            uint32_t n_kept, uint32_t max_prefix_len, uint8_t *out, int variant, void *stream);
+
 /* Synthetic records (tools/synth.py documents the integer hash): rows row0..row0+n_rows-1. */
 int pgb_dev_synth_records(uint8_t *records, uint64_t pitch, uint64_t seed, uint64_t row0, uint64_t n_rows,
                           uint32_t n_samples, void *stream);

@@ -50,6 +50,8 @@ struct pgb_k2_params {
     uint32_t tile_bytes; // multiple of 512
     uint32_t row_bytes_hint; // keep-all: bytes of a record worth prefetching (R + 1)
     uint32_t kidx_vec;       // kidx is 16-byte aligned: index reads may be vectorised
+    uint32_t sfx;            // bytes appended to every prefix after its prefix_blob bytes (little-endian), e.g. "\tGT"
+    uint32_t sfx_len;        // 0..4; pgb_line_meta::pfx_len includes it
 };
 
 struct pgb_u4 {
@@ -339,10 +341,14 @@ PGB_DEV void pgb_k2_item(const pgb_k2_params &p, const pgb_line_meta &m, uint32_
     if (b0 >= b1) { b0 = a_le; b1 = a_le; } // no aligned chunk inside the GT text: bytes only
     const uint8_t *row = p.records + m.rec_off;
 
-    { // prefix bytes (pfile.rs:157-161)
+    { // prefix bytes (pfile.rs:157-161): P - sfx_len bytes of the blob, then the suffix
         const uint8_t *pfx = p.prefix_blob + m.pfx_off;
+        const uint64_t D = P - p.sfx_len;
         const uint64_t lo = a_ls > t0 ? a_ls : t0, hi = a_gs < t1 ? a_gs : t1;
-        for (uint64_t a = lo + lane; a < hi; a += 32) pgb_st8(a, pgb_ld8(pfx + (a - a_ls)));
+        for (uint64_t a = lo + lane; a < hi; a += 32) {
+            const uint64_t x = a - a_ls;
+            pgb_st8(a, x < D ? pgb_ld8(pfx + x) : (p.sfx >> (8u * (uint32_t)(x - D))) & 0xFFu);
+        }
     }
     if (b0 < b1) {
         // <= 15 GT bytes in front of the first aligned chunk (lanes 0-15) and <= 15 GT bytes + the
@@ -363,7 +369,11 @@ PGB_DEV void pgb_k2_item(const pgb_k2_params &p, const pgb_line_meta &m, uint32_
 // destination-aligned 16-byte chunks are copied with aligned 32-bit source reads re-phased by the
 // source/destination misalignment (constant per line), and only the <= 15 bytes on either side are
 // byte stores.
-PGB_DEV void pgb_copy_prefix(const uint8_t *src, uint64_t a_ls, uint32_t al, uint32_t P, uint32_t lane, int hint) {
+PGB_DEV void pgb_copy_prefix(const uint8_t *src, uint64_t a_ls, uint32_t al, uint32_t PS, uint32_t sfx, uint32_t sfx_len,
+                             uint32_t lane, int hint) {
+    // the last sfx_len bytes of the prefix are the constant suffix ("\tGT" when src is a raw .pvar row)
+    const uint32_t P = PS - sfx_len;
+    if (lane < sfx_len) pgb_st8(a_ls + P + lane, (sfx >> (8u * lane)) & 0xFFu);
     if (P < 64u) {
         for (uint32_t x = lane; x < P; x += 32) pgb_st8(a_ls + x, pgb_ld8(src + x));
         return;
@@ -408,7 +418,7 @@ PGB_DEV void pgb_k2_line(const pgb_k2_params &p, const pgb_line_meta &m, uint32_
     const uint32_t al = (uint32_t)a_ls & 15u;
     const uint32_t x_gs = P, x_ge = P + K4, x_le = x_ge + 1u;
     const uint8_t *row = p.records + m.rec_off;
-    pgb_copy_prefix(p.prefix_blob + m.pfx_off, a_ls, al, P, lane, HINT);
+    pgb_copy_prefix(p.prefix_blob + m.pfx_off, a_ls, al, P, p.sfx, p.sfx_len, lane, HINT);
     // [xb0, xb1): the part of the GT text made of whole 16-byte-aligned chunks
     const uint32_t yb0 = (al + x_gs + 15u) & ~15u, yb1 = (al + x_ge) & ~15u; // relative to a_ls - al
     const uint32_t xb0 = yb0 - al, xb1 = yb1 - al;                          // (xb1 is only used when yb0 < yb1)

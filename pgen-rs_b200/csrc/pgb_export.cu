@@ -613,8 +613,8 @@ int run_device_inner(Job *job, DeviceWork *w, std::deque<Pending> &q, std::mutex
                                      (const uint64_t *)(d_stage + lay.off_pos), job->prefix_off[ch.a], n, (uint32_t)K, R,
                                      s.d_meta, s.d_scratch, st);
         if (rc) return rc;
-        rc = pgb_dev_format_lines(d_records, s.d_meta, n, d_stage + lay.pfx_pos, gather ? c->d_kidx : nullptr, (uint32_t)K,
-                                  ch.max_pfx, s.d_out, job->variant, st);
+        rc = pgb_dev_format_lines_ex(d_records, R, s.d_meta, n, d_stage + lay.pfx_pos, 0, 0, gather ? c->d_kidx : nullptr,
+                                     (uint32_t)K, ch.max_pfx, s.d_out, job->variant, st);
         if (rc) return rc;
         CU(cudaEventRecord(s.ev_k1, st));
         w->launches += 4;

@@ -13,6 +13,9 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <algorithm>
+
+#include "k2_batch.cuh"
 #include "k2_core.cuh"
 #include "pgb_internal.h"
 
@@ -71,7 +74,16 @@ __device__ __forceinline__ uint64_t warp_sum_u64(uint64_t v) {
     return v;
 }
 
-__global__ void __launch_bounds__(K1_THREADS) k1_reduce(const uint64_t *__restrict__ prefix_off, uint64_t n,
+// Prefix length of line i: prefix_off[i + 1] - prefix_off[i] (prefixes packed back to back), or, when the
+// prefixes are rows of a raw .pvar image, prefix_len[i] bytes at prefix_off[i]; `fixed` carries the rest of
+// the line (suffix + 4K + 1).
+__device__ __forceinline__ uint64_t k1_plen(const uint64_t *__restrict__ prefix_off, const uint32_t *__restrict__ prefix_len,
+                                            uint64_t i) {
+    return prefix_len ? (uint64_t)prefix_len[i] : prefix_off[i + 1] - prefix_off[i];
+}
+
+__global__ void __launch_bounds__(K1_THREADS) k1_reduce(const uint64_t *__restrict__ prefix_off,
+                                                        const uint32_t *__restrict__ prefix_len, uint64_t n,
                                                         uint64_t fixed, uint64_t *__restrict__ tile_sum) {
     __shared__ uint64_t s_w[K1_THREADS / 32];
     const uint64_t base = (uint64_t)blockIdx.x * K1_TILE;
@@ -79,7 +91,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_reduce(const uint64_t *__restri
 #pragma unroll
     for (int k = 0; k < K1_ITEMS; k++) {
         const uint64_t i = base + (uint64_t)k * K1_THREADS + threadIdx.x;
-        if (i < n) acc += (prefix_off[i + 1] - prefix_off[i]) + fixed;
+        if (i < n) acc += k1_plen(prefix_off, prefix_len, i) + fixed;
     }
     acc = warp_sum_u64(acc);
     if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
@@ -137,23 +149,30 @@ __global__ void __launch_bounds__(1024) k1_scan(uint64_t *__restrict__ tile_sum,
 
 __global__ void __launch_bounds__(K1_THREADS) k1_emit(const uint32_t *__restrict__ var_row,
                                                       const uint64_t *__restrict__ rec_off_in,
-                                                      const uint64_t *__restrict__ prefix_off, uint64_t prefix_base,
-                                                      uint64_t n, uint64_t fixed, uint64_t pitch,
+                                                      const uint64_t *__restrict__ prefix_off,
+                                                      const uint32_t *__restrict__ prefix_len, uint32_t sfx_len,
+                                                      uint64_t prefix_base, uint64_t n, uint64_t fixed, uint64_t pitch,
                                                       const uint64_t *__restrict__ tile_base,
                                                       pgb_line_meta *__restrict__ meta) {
     __shared__ uint64_t s_w[K1_THREADS / 32];
     const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     const uint64_t first = (uint64_t)blockIdx.x * K1_TILE + (uint64_t)threadIdx.x * K1_ITEMS;
     uint64_t po[K1_ITEMS + 1];
+    uint32_t pl[K1_ITEMS];
 #pragma unroll
     for (int k = 0; k <= K1_ITEMS; k++) {
         const uint64_t i = first + k;
-        po[k] = i <= n ? prefix_off[i] : 0;
+        po[k] = (prefix_len ? i < n : i <= n) ? prefix_off[i] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < K1_ITEMS; k++) {
+        const uint64_t i = first + k;
+        pl[k] = i < n ? (prefix_len ? prefix_len[i] : (uint32_t)(po[k + 1] - po[k])) + sfx_len : 0u;
     }
     uint64_t tsum = 0;
 #pragma unroll
     for (int k = 0; k < K1_ITEMS; k++)
-        if (first + k < n) tsum += (po[k + 1] - po[k]) + fixed;
+        if (first + k < n) tsum += pl[k] + fixed;
     uint64_t inc = tsum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -168,7 +187,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_emit(const uint32_t *__restrict
     for (int k = 0; k < K1_ITEMS; k++) {
         const uint64_t i = first + k;
         if (i < n) {
-            const uint64_t P = po[k + 1] - po[k];
+            const uint64_t P = pl[k];
             const uint64_t row = var_row ? (uint64_t)var_row[i] : i;
             uint4 a, b;
             a.x = (uint32_t)off; a.y = (uint32_t)(off >> 32);
@@ -288,6 +307,77 @@ __global__ void __launch_bounds__(K2_THREADS) k2_format_kernel(const pgb_k2_para
     }
 }
 
+// ------------------------------------------------------------ K2 (batch) ---
+// Short lines: a CTA stages B consecutive lines in shared memory (k2_batch.cuh): records in by
+// bulk async copies, kept samples compacted to packed virtual records, text formatted into an
+// image of the batch's contiguous output range, the image out by one bulk async store.
+__device__ __forceinline__ void k2b_mbar_wait(uint8_t *mbar, uint32_t parity) {
+    const uint32_t bar = k2b_smem_addr(mbar);
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
+template <bool GATHER>
+__global__ void __launch_bounds__(K2B_THREADS) k2_batch_kernel(const pgb_k2b_params p) {
+    extern __shared__ __align__(128) uint8_t k2b_smem[];
+    uint8_t *smem = k2b_smem;
+    const pgb_k2b_layout L = pgb_k2b_smem_layout(p.B, p.rowcap, p.vcap, p.outcap, GATHER);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint64_t i0 = (uint64_t)blockIdx.x * p.B;
+    const uint64_t left = p.n_lines - i0;
+    const uint32_t nbl = left < p.B ? (uint32_t)left : p.B;
+    // record bytes that hold kept samples: all of the record, or the span of the kept-sample list
+    uint32_t span_lo = 0, span_len = p.K ? p.R : 0u;
+    if (GATHER && p.K) {
+        span_lo = __ldg(p.kidx) >> 2;
+        span_len = (__ldg(p.kidx + (p.K - 1u)) >> 2) + 1u - span_lo;
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k2b_smem_addr(smem)), "r"(nbl) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    k2b_build_lut(smem, L, tid);
+    __syncthreads();
+    k2b_phase_meta(p, smem, L, i0, nbl, tid, span_lo, span_len);
+    __syncthreads();
+    k2b_phase_prefix(p, smem, L, nbl, warp, lane);
+    if (span_len) k2b_mbar_wait(smem, 0);
+    if (GATHER) {
+        k2b_phase_compact(p, smem, L, nbl, tid, span_lo);
+        __syncthreads();
+    }
+    k2b_phase_format<GATHER>(p, smem, L, nbl, warp, lane);
+    // the image was written through the generic proxy; the bulk store reads it through the async proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const uint32_t *lo = reinterpret_cast<const uint32_t *>(smem + L.lo);
+    const uint32_t phase = lo[0], T = lo[nbl] - phase;
+    const uint64_t g_al = (uint64_t)(uintptr_t)p.out + *reinterpret_cast<const uint64_t *>(smem + 8) - phase;
+    const uint8_t *outb = smem + L.outb;
+    const uint32_t h0 = phase ? 16u : 0u, h1 = (phase + T) & ~15u;
+    if (p.store_mode == 0) {
+        if (tid == 0 && h0 < h1) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g_al + h0),
+                         "r"(k2b_smem_addr(outb + h0)), "r"(h1 - h0)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    } else {
+        for (uint32_t a = h0 + 16u * tid; a < h1; a += 16u * K2B_THREADS) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(outb + a);
+            pgb_st16(g_al + a, v.x, v.y, v.z, v.w, 1);
+        }
+    }
+    if (warp == 1) k2b_store_edges(g_al, outb, phase, T, lane);
+    // shared memory must stay intact until the bulk store has read it
+    if (p.store_mode == 0 && tid == 0 && h0 < h1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // -------------------------------------------------------------- synth ------
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
     uint64_t z = x + 0x9E3779B97F4A7C15ull;
@@ -383,16 +473,16 @@ extern "C" uint64_t pgb_dev_index_scratch_bytes(uint64_t n_lines) {
 }
 
 static int index_lines_impl(const uint32_t *var_row, const uint64_t *rec_off_in, const uint64_t *prefix_off,
-                            uint64_t prefix_base, uint64_t n_lines, uint32_t n_kept, uint64_t pitch, pgb_line_meta *meta,
-                            void *scratch, void *stream) {
-    if (!prefix_off || !meta || !scratch) return PGB_E_ARG;
+                            const uint32_t *prefix_len, uint32_t sfx_len, uint64_t prefix_base, uint64_t n_lines,
+                            uint32_t n_kept, uint64_t pitch, pgb_line_meta *meta, void *scratch, void *stream) {
+    if (!prefix_off || !meta || !scratch || sfx_len > 4) return PGB_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    const uint64_t fixed = 4ull * n_kept + 1ull;
+    const uint64_t fixed = 4ull * n_kept + 1ull; // pl[] in k1_emit already includes the suffix
     const uint64_t tiles = (n_lines + K1_TILE - 1) / K1_TILE;
     uint64_t *tile_sum = (uint64_t *)scratch;
     if (tiles > 0x7fffffffull) return PGB_E_ARG;
     if (tiles) {
-        k1_reduce<<<(unsigned)tiles, K1_THREADS, 0, st>>>(prefix_off, n_lines, fixed, tile_sum);
+        k1_reduce<<<(unsigned)tiles, K1_THREADS, 0, st>>>(prefix_off, prefix_len, n_lines, fixed + sfx_len, tile_sum);
         int rc = check_launch("k1_reduce");
         if (rc) return rc;
     }
@@ -400,8 +490,8 @@ static int index_lines_impl(const uint32_t *var_row, const uint64_t *rec_off_in,
     int rc = check_launch("k1_scan");
     if (rc) return rc;
     if (tiles) {
-        k1_emit<<<(unsigned)tiles, K1_THREADS, 0, st>>>(var_row, rec_off_in, prefix_off, prefix_base, n_lines, fixed, pitch,
-                                                       tile_sum, meta);
+        k1_emit<<<(unsigned)tiles, K1_THREADS, 0, st>>>(var_row, rec_off_in, prefix_off, prefix_len, sfx_len, prefix_base,
+                                                       n_lines, fixed, pitch, tile_sum, meta);
         rc = check_launch("k1_emit");
     }
     return rc;
@@ -410,14 +500,23 @@ static int index_lines_impl(const uint32_t *var_row, const uint64_t *rec_off_in,
 extern "C" int pgb_dev_index_lines(const uint32_t *var_row, const uint64_t *prefix_off, uint64_t prefix_base,
                                    uint64_t n_lines, uint32_t n_kept, uint64_t pitch, pgb_line_meta *meta,
                                    void *scratch, void *stream) {
-    return index_lines_impl(var_row, nullptr, prefix_off, prefix_base, n_lines, n_kept, pitch, meta, scratch, stream);
+    return index_lines_impl(var_row, nullptr, prefix_off, nullptr, 0, prefix_base, n_lines, n_kept, pitch, meta, scratch,
+                            stream);
 }
 
 extern "C" int pgb_dev_index_lines_off(const uint64_t *rec_off, const uint64_t *prefix_off, uint64_t prefix_base,
                                        uint64_t n_lines, uint32_t n_kept, pgb_line_meta *meta, void *scratch,
                                        void *stream) {
     if (!rec_off) return PGB_E_ARG;
-    return index_lines_impl(nullptr, rec_off, prefix_off, prefix_base, n_lines, n_kept, 0, meta, scratch, stream);
+    return index_lines_impl(nullptr, rec_off, prefix_off, nullptr, 0, prefix_base, n_lines, n_kept, 0, meta, scratch, stream);
+}
+
+extern "C" int pgb_dev_index_lines_ex(const uint32_t *var_row, const uint64_t *rec_off, uint64_t pitch,
+                                      const uint64_t *prefix_off, const uint32_t *prefix_len, uint32_t suffix_len,
+                                      uint64_t prefix_base, uint64_t n_lines, uint32_t n_kept, pgb_line_meta *meta,
+                                      void *scratch, void *stream) {
+    return index_lines_impl(rec_off ? nullptr : var_row, rec_off, prefix_off, prefix_len, suffix_len, prefix_base, n_lines,
+                            n_kept, pitch, meta, scratch, stream);
 }
 
 template <bool GATHER, int HINT, int REPL, int IPW, bool ONE>
@@ -450,15 +549,81 @@ static int launch_k2_ipw(const pgb_k2_params &p, cudaStream_t st, int ipw) {
     }
 }
 
-// variant: bits 0-3  store hint (0 => .cs streaming, the measured best; 2 => default write-back)
-//          bits 4-7  LUT copies (0 => default, see below; 1 => 8 interleaved bank-conflict-free copies; 2 => one)
-//          bits 8-11 items per warp (0 => default; 1, 2, 4, 8)
+// Batch path (k2_batch.cuh): plan the shared-memory budget; returns false when the lines are too long for it.
+static bool plan_k2_batch(uint32_t K, uint32_t R, bool gather, uint32_t max_prefix_len, int variant, pgb_k2b_params *bp,
+                          uint32_t *smem_bytes) {
+    const int bsel = (variant >> 20) & 0xF, msel = (variant >> 24) & 0xF;
+    const uint64_t max_line = (uint64_t)max_prefix_len + 4ull * K + 1ull;
+    const uint64_t budget = msel ? (uint64_t)msel * 16384ull : 54ull * 1024ull; // default: four CTAs per SM
+    const uint64_t rowcap = ((uint64_t)R + 31ull + 15ull) & ~15ull;
+    const uint64_t vcap = gather ? (((uint64_t)(K + 3u) / 4ull + 2ull + 15ull) & ~15ull) : 0ull;
+    const uint64_t per_line = rowcap + vcap + max_line + 20ull;
+    const uint64_t fixed = 16 + 128 + 4 + 128 + 48;
+    if (budget <= fixed + 4 * per_line) return false;
+    uint64_t B = (budget - fixed) / per_line;
+    if (B > 32) B = 32;
+    if (bsel) B = std::min<uint64_t>(B, 4ull * bsel);
+    if (B < 4) return false;
+    bp->K = K;
+    bp->R = R;
+    bp->B = (uint32_t)B;
+    bp->rowcap = (uint32_t)rowcap;
+    bp->vcap = (uint32_t)vcap;
+    bp->outcap = (uint32_t)((B * max_line + 32ull + 15ull) & ~15ull);
+    bp->store_mode = (variant >> 28) & 1;
+    *smem_bytes = pgb_k2b_smem_layout(bp->B, bp->rowcap, bp->vcap, bp->outcap, gather).total;
+    return *smem_bytes <= 227u * 1024u;
+}
+
+template <bool GATHER>
+static int launch_k2_batch(const pgb_k2b_params &bp, uint32_t smem_bytes, cudaStream_t st) {
+    const uint64_t blocks = (bp.n_lines + bp.B - 1) / bp.B;
+    if (blocks > 0x7fffffffull) return PGB_E_ARG;
+    cudaError_t e = cudaFuncSetAttribute(k2_batch_kernel<GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) {
+        pgb_set_error("cudaFuncSetAttribute(k2_batch_kernel, %u bytes): %s", smem_bytes, cudaGetErrorString(e));
+        return PGB_E_CUDA;
+    }
+    k2_batch_kernel<GATHER><<<(unsigned)blocks, K2B_THREADS, smem_bytes, st>>>(bp);
+    return check_launch("k2_batch_kernel");
+}
+
+// variant: bits 0-3   store hint (0 => .cs streaming, the measured best; 2 => default write-back)
+//          bits 4-7   LUT copies (0 => default, see below; 1 => 8 interleaved bank-conflict-free copies; 2 => one)
+//          bits 8-11  items per warp (0 => default; 1, 2, 4, 8)
 //          bits 12-15 tile size = 4 KiB << n (0 => 16 KiB)
-extern "C" int pgb_dev_format_lines(const uint8_t *records, const pgb_line_meta *meta, uint64_t n_lines,
-                                    const uint8_t *prefix_blob, const uint32_t *kidx, uint32_t n_kept,
-                                    uint32_t max_prefix_len, uint8_t *out, int variant, void *stream) {
+//          bits 16-19 batch path (k2_batch.cuh): 0 => default (gather launches whose batch fits), 1 => off, 2 => on
+//                     whenever the batch fits (also keep-all)
+//          bits 20-23 batch path: lines per CTA <= 4 * n (0 => up to 32)
+//          bits 24-27 batch path: shared-memory budget = n * 16 KiB (0 => 54 KiB, four CTAs per SM)
+//          bit  28    batch path: 16-byte st.global stores instead of the bulk async store
+extern "C" int pgb_dev_format_lines_ex(const uint8_t *records, uint32_t record_bytes, const pgb_line_meta *meta,
+                                       uint64_t n_lines, const uint8_t *prefix_blob, uint32_t suffix, uint32_t suffix_len,
+                                       const uint32_t *kidx, uint32_t n_kept, uint32_t max_prefix_len, uint8_t *out,
+                                       int variant, void *stream) {
     if (n_lines == 0) return PGB_OK;
-    if (!records || !meta || !out || (!prefix_blob && max_prefix_len)) return PGB_E_ARG;
+    if (!records || !meta || !out || (!prefix_blob && max_prefix_len > suffix_len) || suffix_len > 4) return PGB_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool gatherp = kidx != nullptr;
+    const uint32_t kidx_vec = kidx && ((uintptr_t)kidx & 15u) == 0 ? 1u : 0u;
+    if (!gatherp) record_bytes = (n_kept + 3u) / 4u; // keep-all: n_kept is the file's sample count
+    const int bmode = (variant >> 16) & 0xF;
+    if (bmode != 1 && (record_bytes || n_kept == 0) && (gatherp || bmode == 2)) {
+        pgb_k2b_params bp;
+        uint32_t smem_bytes = 0;
+        if (plan_k2_batch(n_kept, record_bytes, gatherp, max_prefix_len, variant, &bp, &smem_bytes)) {
+            bp.records = records;
+            bp.meta = meta;
+            bp.prefix_blob = prefix_blob;
+            bp.kidx = kidx;
+            bp.out = out;
+            bp.n_lines = n_lines;
+            bp.sfx = suffix;
+            bp.sfx_len = suffix_len;
+            bp.kidx_vec = kidx_vec;
+            return gatherp ? launch_k2_batch<true>(bp, smem_bytes, st) : launch_k2_batch<false>(bp, smem_bytes, st);
+        }
+    }
     pgb_k2_params p;
     p.records = records;
     p.meta = meta;
@@ -467,6 +632,8 @@ extern "C" int pgb_dev_format_lines(const uint8_t *records, const pgb_line_meta 
     p.out = out;
     p.n_lines = n_lines;
     p.K = n_kept;
+    p.sfx = suffix;
+    p.sfx_len = suffix_len;
     const int hint = (variant & 0xF) == 2 ? 0 : 1;
     const int lsel = (variant >> 4) & 0xF;
     int ipw = (variant >> 8) & 0xF;
@@ -479,21 +646,26 @@ extern "C" int pgb_dev_format_lines(const uint8_t *records, const pgb_line_meta 
     // Defaults measured on B200 (profiles/README.md, 2.5 GB of output per shape): lines > 7 KiB (and tiled
     // lines) -> 8 conflict-free LUT copies, one item per warp; 3-7 KiB -> one LUT copy (the 32 KB table costs
     // more to build than it saves), one item per warp; <= 3 KiB and gather -> one copy, four items per warp.
-    const bool gatherp = kidx != nullptr;
     const bool small_lines = nt == 1 && max_line <= 3072, mid_lines = nt == 1 && max_line <= 7168;
     const bool repl8 = lsel == 1 || (lsel == 0 && !gatherp && !mid_lines);
     if (ipw == 0) ipw = (gatherp || small_lines) ? 4 : 1;
     // bytes of a record worth prefetching: all of it for keep-all, up to the last kept sample otherwise
     p.row_bytes_hint = kidx ? 0u : (n_kept + 3u) / 4u + 1u;
-    p.kidx_vec = kidx && ((uintptr_t)kidx & 15u) == 0 ? 1u : 0u;
-    cudaStream_t st = (cudaStream_t)stream;
-    const bool g = kidx != nullptr;
+    p.kidx_vec = kidx_vec;
+    const bool g = gatherp;
     if (hint == 1) {
         if (repl8) return g ? launch_k2_ipw<true, 1, 8>(p, st, ipw) : launch_k2_ipw<false, 1, 8>(p, st, ipw);
         return g ? launch_k2_ipw<true, 1, 1>(p, st, ipw) : launch_k2_ipw<false, 1, 1>(p, st, ipw);
     }
     if (repl8) return g ? launch_k2_ipw<true, 0, 8>(p, st, ipw) : launch_k2_ipw<false, 0, 8>(p, st, ipw);
     return g ? launch_k2_ipw<true, 0, 1>(p, st, ipw) : launch_k2_ipw<false, 0, 1>(p, st, ipw);
+}
+
+extern "C" int pgb_dev_format_lines(const uint8_t *records, const pgb_line_meta *meta, uint64_t n_lines,
+                                    const uint8_t *prefix_blob, const uint32_t *kidx, uint32_t n_kept,
+                                    uint32_t max_prefix_len, uint8_t *out, int variant, void *stream) {
+    return pgb_dev_format_lines_ex(records, 0, meta, n_lines, prefix_blob, 0, 0, kidx, n_kept, max_prefix_len, out, variant,
+                                   stream);
 }
 
 extern "C" int pgb_dev_synth_records(uint8_t *records, uint64_t pitch, uint64_t seed, uint64_t row0, uint64_t n_rows,

@@ -98,6 +98,8 @@ SYMBOLS = {
     "pgb_dev_index_lines": (_i, [_vp, _vp, _u64, _u64, _u32, _u64, _vp, _vp, _vp]),
     "pgb_dev_index_lines_off": (_i, [_vp, _vp, _u64, _u64, _u32, _vp, _vp, _vp]),
     "pgb_dev_format_lines": (_i, [_vp, _vp, _u64, _vp, _vp, _u32, _u32, _vp, _i, _vp]),
+    "pgb_dev_index_lines_ex": (_i, [_vp, _vp, _u64, _vp, _vp, _u32, _u64, _u64, _u32, _vp, _vp, _vp]),
+    "pgb_dev_format_lines_ex": (_i, [_vp, _u32, _vp, _u64, _vp, _u32, _u32, _vp, _u32, _u32, _vp, _i, _vp]),
     "pgb_dev_synth_records": (_i, [_vp, _u64, _u64, _u64, _u64, _u32, _vp]),
     "pgb_dev_fill": (_i, [_vp, _u64, _i, _vp]),
     "pgb_dev_fill_pattern": (_i, [_vp, _u64, _u32, _u32, _u32, _u32, _i, _vp]),
@@ -271,13 +273,14 @@ def pgen10_index(path: str, want_index: bool = True):
 # ---- device-resident helpers (torch tensors supply device memory and streams) ----
 
 def dev_format(records, pitch: int, var_row, prefix_blob, prefix_off, kidx, n_kept: int, max_prefix_len: int, out,
-               meta, scratch, variant: int = 0, stream: int = 0, prefix_base: int = 0, n_lines: Optional[int] = None):
+               meta, scratch, variant: int = 0, stream: int = 0, prefix_base: int = 0, n_lines: Optional[int] = None,
+               record_bytes: Optional[int] = None):
     """K1 + K2 on torch CUDA tensors (raw data_ptr()s are passed through the C ABI)."""
     n = (prefix_off.numel() - 1) if n_lines is None else n_lines
     rc = lib.pgb_dev_index_lines(None if var_row is None else var_row.data_ptr(), prefix_off.data_ptr(), prefix_base, n,
                                  n_kept, pitch, meta.data_ptr(), scratch.data_ptr(), stream)
     _check(rc, "pgb_dev_index_lines")
-    rc = lib.pgb_dev_format_lines(records.data_ptr(), meta.data_ptr(), n, prefix_blob.data_ptr(),
-                                  None if kidx is None else kidx.data_ptr(), n_kept, max_prefix_len, out.data_ptr(),
-                                  variant, stream)
-    _check(rc, "pgb_dev_format_lines")
+    rc = lib.pgb_dev_format_lines_ex(records.data_ptr(), pitch if record_bytes is None else record_bytes, meta.data_ptr(), n,
+                                     prefix_blob.data_ptr(), 0, 0, None if kidx is None else kidx.data_ptr(), n_kept,
+                                     max_prefix_len, out.data_ptr(), variant, stream)
+    _check(rc, "pgb_dev_format_lines_ex")

@@ -82,13 +82,20 @@ def k2sim():
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "k2sim.so")
     srcs = [os.path.join(ROOT, "tests", "hostsim", "k2_hostsim.cpp"),
-            os.path.join(ROOT, "pgen-rs_b200", "csrc", "k2_core.cuh")]
+            os.path.join(ROOT, "pgen-rs_b200", "csrc", "k2_core.cuh"),
+            os.path.join(ROOT, "pgen-rs_b200", "csrc", "k2_batch.cuh")]
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         _run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-shared", "-fPIC", "-o", so, srcs[0]])
     lib = ctypes.CDLL(so)
     lib.sim_format_lines.restype = ctypes.c_int
     lib.sim_format_lines.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int]
+    lib.sim_format_lines_sfx.restype = ctypes.c_int
+    lib.sim_format_lines_sfx.argtypes = lib.sim_format_lines.argtypes + [ctypes.c_uint32, ctypes.c_uint32]
+    lib.sim_format_lines_batch.restype = ctypes.c_int
+    lib.sim_format_lines_batch.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint64,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p,
+                                           ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int]
     return lib
 
 

@@ -9,16 +9,21 @@
 
 #include <vector>
 
+#include "../../pgen-rs_b200/csrc/k2_batch.cuh"
 #include "../../pgen-rs_b200/csrc/k2_core.cuh"
 
-extern "C" int sim_format_lines(const uint8_t *records, uint64_t pitch, const uint32_t *var_row, uint64_t n_lines,
-                                const uint8_t *prefix_blob, const uint64_t *prefix_off, const uint32_t *kidx,
-                                uint32_t K, uint8_t *out, int variant) {
-    std::vector<pgb_line_meta> meta(n_lines + 1);
+extern "C" int sim_format_lines_sfx(const uint8_t *records, uint64_t pitch, const uint32_t *var_row, uint64_t n_lines,
+                                    const uint8_t *prefix_blob, const uint64_t *prefix_off, const uint32_t *kidx,
+                                    uint32_t K, uint8_t *out, int variant, uint32_t sfx, uint32_t sfx_len);
+
+// What K1 computes.  sfx_len > 0: the last sfx_len bytes of every prefix are the constant suffix `sfx`
+// and prefix_blob holds only the bytes in front of it (prefix_off[i+1] - prefix_off[i] of them).
+static uint32_t sim_meta(std::vector<pgb_line_meta> &meta, uint64_t pitch, const uint32_t *var_row, uint64_t n_lines,
+                         const uint64_t *prefix_off, uint32_t K, uint32_t sfx_len) {
     uint64_t off = 0;
     uint32_t maxp = 0;
     for (uint64_t i = 0; i < n_lines; i++) {
-        uint64_t P = prefix_off[i + 1] - prefix_off[i];
+        uint64_t P = prefix_off[i + 1] - prefix_off[i] + sfx_len;
         meta[i].line_off = off;
         meta[i].rec_off = (var_row ? var_row[i] : i) * pitch;
         meta[i].pfx_off = prefix_off[i] - prefix_off[0];
@@ -28,6 +33,81 @@ extern "C" int sim_format_lines(const uint8_t *records, uint64_t pitch, const ui
         off += P + 4ull * K + 1;
     }
     meta[n_lines].line_off = off;
+    return maxp;
+}
+
+// The batch path (k2_batch.cuh), phase by phase with a loop over the CTA's threads standing in
+// for each __syncthreads()-delimited phase; bulk copies are memcpy()s.
+extern "C" int sim_format_lines_batch(const uint8_t *records, uint64_t pitch, uint32_t R, const uint32_t *var_row,
+                                      uint64_t n_lines, const uint8_t *prefix_blob, const uint64_t *prefix_off,
+                                      const uint32_t *kidx, uint32_t K, uint8_t *out, uint32_t B, uint32_t sfx,
+                                      uint32_t sfx_len, int kidx_vec) {
+    std::vector<pgb_line_meta> meta(n_lines + 1);
+    const uint32_t maxp = sim_meta(meta, pitch, var_row, n_lines, prefix_off, K, sfx_len);
+    const bool gather = kidx != nullptr;
+    pgb_k2b_params p;
+    p.records = records;
+    p.meta = meta.data();
+    p.prefix_blob = prefix_blob + prefix_off[0];
+    p.kidx = kidx;
+    p.out = out;
+    p.n_lines = n_lines;
+    p.K = K;
+    p.R = R;
+    p.B = B;
+    p.rowcap = pgb_k2b_align(R + 31u, 16);
+    p.vcap = gather ? pgb_k2b_align((K + 3u) / 4u + 2u, 16) : 0u;
+    const uint64_t max_line = (uint64_t)maxp + 4ull * K + 1ull;
+    p.outcap = pgb_k2b_align((uint32_t)(B * max_line + 32u), 16);
+    p.sfx = sfx;
+    p.sfx_len = sfx_len;
+    p.kidx_vec = kidx_vec ? 1u : 0u;
+    p.store_mode = 0;
+    const pgb_k2b_layout L = pgb_k2b_smem_layout(p.B, p.rowcap, p.vcap, p.outcap, gather);
+    std::vector<uint8_t> smem_store(L.total + 256);
+    uint8_t *smem = smem_store.data() + ((128 - ((uintptr_t)smem_store.data() & 127)) & 127);
+    for (uint64_t i0 = 0; i0 < n_lines; i0 += B) {
+        memset(smem, 0xCD, L.total); // stale shared memory
+        const uint32_t nbl = (uint32_t)(n_lines - i0 < B ? n_lines - i0 : B);
+        uint32_t span_lo = 0, span_len = K ? R : 0u;
+        if (gather && K) {
+            span_lo = kidx[0] >> 2;
+            span_len = (kidx[K - 1] >> 2) + 1u - span_lo;
+        }
+        for (uint32_t t = 0; t < K2B_THREADS; t++) k2b_build_lut(smem, L, t);
+        for (uint32_t t = 0; t < K2B_THREADS; t++) k2b_phase_meta(p, smem, L, i0, nbl, t, span_lo, span_len);
+        for (uint32_t t = 0; t < K2B_THREADS; t++) k2b_phase_prefix(p, smem, L, nbl, t >> 5, t & 31u);
+        if (gather)
+            for (uint32_t t = 0; t < K2B_THREADS; t++) k2b_phase_compact(p, smem, L, nbl, t, span_lo);
+        for (uint32_t t = 0; t < K2B_THREADS; t++) {
+            if (gather) k2b_phase_format<true>(p, smem, L, nbl, t >> 5, t & 31u);
+            else k2b_phase_format<false>(p, smem, L, nbl, t >> 5, t & 31u);
+        }
+        const uint32_t *lo = reinterpret_cast<const uint32_t *>(smem + L.lo);
+        const uint32_t phase = lo[0], T = lo[nbl] - phase;
+        uint64_t base;
+        memcpy(&base, smem + 8, 8);
+        const uint64_t g_al = (uint64_t)(uintptr_t)p.out + base - phase;
+        if (g_al & 15u) return -1;
+        const uint8_t *outb = smem + L.outb;
+        const uint32_t h0 = phase ? 16u : 0u, h1 = (phase + T) & ~15u;
+        if (h0 < h1) memcpy((void *)(uintptr_t)(g_al + h0), outb + h0, h1 - h0); // the bulk store
+        for (uint32_t lane = 0; lane < 32; lane++) k2b_store_edges(g_al, outb, phase, T, lane);
+    }
+    return 0;
+}
+
+extern "C" int sim_format_lines(const uint8_t *records, uint64_t pitch, const uint32_t *var_row, uint64_t n_lines,
+                                const uint8_t *prefix_blob, const uint64_t *prefix_off, const uint32_t *kidx,
+                                uint32_t K, uint8_t *out, int variant) {
+    return sim_format_lines_sfx(records, pitch, var_row, n_lines, prefix_blob, prefix_off, kidx, K, out, variant, 0, 0);
+}
+
+extern "C" int sim_format_lines_sfx(const uint8_t *records, uint64_t pitch, const uint32_t *var_row, uint64_t n_lines,
+                                    const uint8_t *prefix_blob, const uint64_t *prefix_off, const uint32_t *kidx,
+                                    uint32_t K, uint8_t *out, int variant, uint32_t sfx, uint32_t sfx_len) {
+    std::vector<pgb_line_meta> meta(n_lines + 1);
+    const uint32_t maxp = sim_meta(meta, pitch, var_row, n_lines, prefix_off, K, sfx_len);
     pgb_k2_params p;
     p.records = records;
     p.meta = meta.data();
@@ -36,6 +116,8 @@ extern "C" int sim_format_lines(const uint8_t *records, uint64_t pitch, const ui
     p.out = out;
     p.n_lines = n_lines;
     p.K = K;
+    p.sfx = sfx;
+    p.sfx_len = sfx_len;
     const int hint = variant & 0xF;
     const int lsel = (variant >> 4) & 0xF;
     const int single = lsel == 1 || (lsel == 0 && kidx == nullptr); // 1 => 8 LUT copies
