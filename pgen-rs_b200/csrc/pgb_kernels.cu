@@ -308,9 +308,10 @@ __global__ void __launch_bounds__(K2_THREADS) k2_format_kernel(const pgb_k2_para
 }
 
 // ------------------------------------------------------------ K2 (batch) ---
-// Short lines: a CTA stages B consecutive lines in shared memory (k2_batch.cuh): records in by
-// bulk async copies, kept samples compacted to packed virtual records, text formatted into an
-// image of the batch's contiguous output range, the image out by one bulk async store.
+// Short lines: a persistent CTA walks batches of B consecutive lines through two shared-memory
+// stages (k2_batch.cuh): records and prefixes of batch n+1 arrive by bulk async copies while batch
+// n is compacted and formatted into an image of its contiguous output range, and the image of
+// batch n leaves by one bulk async store while batch n+1 is formatted into the other image.
 __device__ __forceinline__ void k2b_mbar_wait(uint8_t *mbar, uint32_t parity) {
     const uint32_t bar = k2b_smem_addr(mbar);
     uint32_t done;
@@ -326,56 +327,96 @@ template <bool GATHER>
 __global__ void __launch_bounds__(K2B_THREADS) k2_batch_kernel(const pgb_k2b_params p) {
     extern __shared__ __align__(128) uint8_t k2b_smem[];
     uint8_t *smem = k2b_smem;
-    const pgb_k2b_layout L = pgb_k2b_smem_layout(p.B, p.rowcap, p.vcap, p.outcap, GATHER);
+    const pgb_k2b_layout L = pgb_k2b_smem_layout(p.B, p.rowcap, p.pcap, p.vcap, p.outcap, GATHER);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint64_t i0 = (uint64_t)blockIdx.x * p.B;
-    const uint64_t left = p.n_lines - i0;
-    const uint32_t nbl = left < p.B ? (uint32_t)left : p.B;
     // record bytes that hold kept samples: all of the record, or the span of the kept-sample list
     uint32_t span_lo = 0, span_len = p.K ? p.R : 0u;
+    pgb_k2b_plan plan0 = {{0u, 0u, 0u, 0u}};
     if (GATHER && p.K) {
         span_lo = __ldg(p.kidx) >> 2;
         span_len = (__ldg(p.kidx + (p.K - 1u)) >> 2) + 1u - span_lo;
+        const uint32_t nb = (p.K + 3u) >> 2, jl = tid & (k2b_compact_width(nb) - 1u);
+        if (nb <= K2B_THREADS && jl < nb) plan0 = k2b_load_plan(p, jl, span_lo);
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k2b_smem_addr(smem)), "r"(nbl) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k2b_smem_addr(smem)), "r"(p.B) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k2b_smem_addr(smem + 8)), "r"(p.B) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     k2b_build_lut(smem, L, tid);
-    __syncthreads();
-    k2b_phase_meta(p, smem, L, i0, nbl, tid, span_lo, span_len);
-    __syncthreads();
-    k2b_phase_prefix(p, smem, L, nbl, warp, lane);
-    if (span_len) k2b_mbar_wait(smem, 0);
-    if (GATHER) {
-        k2b_phase_compact(p, smem, L, nbl, tid, span_lo);
+
+    // batches of this CTA: bt, bt + gridDim.x, ...; line range of batch b: [b * B, min(n_lines, (b+1) * B))
+    auto lines_of = [&](uint64_t b) -> uint32_t {
+        if (b >= p.n_batches) return 0u;
+        const uint64_t left = p.n_lines - b * p.B;
+        return left < p.B ? (uint32_t)left : p.B;
+    };
+    // the pgb_line_meta of this thread's line in a batch (thread nbl: the end of the batch) and the batch's body offset
+    pgb_line_meta m_next;
+    uint64_t base_next = 0;
+    auto fetch_meta = [&](uint64_t b) {
+        const uint32_t nbl = lines_of(b);
+        if (nbl && tid <= nbl) {
+            m_next = pgb_ld_meta(p.meta + b * p.B + tid);
+            base_next = k2b_ld_u64(&p.meta[b * p.B].line_off);
+        }
+    };
+    uint64_t bt = blockIdx.x;
+    fetch_meta(bt);
+    __syncthreads(); // mbarriers initialised, table built
+    {
+        const uint32_t nbl = lines_of(bt);
+        if (nbl) k2b_phase_issue(p, smem, L, 0, nbl, tid, m_next, base_next, span_lo, span_len);
+    }
+    fetch_meta(bt + gridDim.x);
+    bool store_pending = false; // thread 0: a bulk store group is in flight
+    for (uint32_t n = 0;; n++, bt += gridDim.x) {
+        const uint32_t stage = n & 1u;
+        const uint32_t nbl = lines_of(bt);
+        if (!nbl) break;
+        // the image about to be rewritten (batch n-2's) must have left shared memory
+        if (tid == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncthreads(); // tables of this stage visible; the other stage's buffers are free
+        {   // INPUT of the next batch, then the index read of the one after
+            const uint32_t nbl1 = lines_of(bt + gridDim.x);
+            if (nbl1) k2b_phase_issue(p, smem, L, stage ^ 1u, nbl1, tid, m_next, base_next, span_lo, span_len);
+            fetch_meta(bt + 2ull * gridDim.x);
+        }
+        const uint8_t *tab = smem + L.tab[stage];
+        const uint32_t *ols = reinterpret_cast<const uint32_t *>(tab + L.t_ols);
+        const uint32_t phase = ols[0], T = ols[nbl] - phase;
+        const uint64_t g_al = (uint64_t)(uintptr_t)p.out + *reinterpret_cast<const uint64_t *>(tab) - phase;
+        k2b_mbar_wait(smem + 8u * stage, (n >> 1) & 1u);
+        k2b_phase_prefix(p, smem, L, stage, nbl, warp, lane);
+        if (GATHER) {
+            k2b_phase_compact(p, smem, L, stage, nbl, tid, span_lo, plan0);
+            __syncthreads();
+        }
+        k2b_phase_format<GATHER>(p, smem, L, stage, nbl, warp, lane);
+        // the image was written through the generic proxy; the bulk store reads it through the async proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-    }
-    k2b_phase_format<GATHER>(p, smem, L, nbl, warp, lane);
-    // the image was written through the generic proxy; the bulk store reads it through the async proxy
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    const uint32_t *lo = reinterpret_cast<const uint32_t *>(smem + L.lo);
-    const uint32_t phase = lo[0], T = lo[nbl] - phase;
-    const uint64_t g_al = (uint64_t)(uintptr_t)p.out + *reinterpret_cast<const uint64_t *>(smem + 8) - phase;
-    const uint8_t *outb = smem + L.outb;
-    const uint32_t h0 = phase ? 16u : 0u, h1 = (phase + T) & ~15u;
-    if (p.store_mode == 0) {
-        if (tid == 0 && h0 < h1) {
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g_al + h0),
-                         "r"(k2b_smem_addr(outb + h0)), "r"(h1 - h0)
-                         : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        const uint8_t *outb = smem + L.outb[stage];
+        const uint32_t h0 = phase ? 16u : 0u, h1 = (phase + T) & ~15u;
+        if (p.store_mode == 0) {
+            if (tid == 0) { // one group per batch (possibly empty), so that wait_group.read 1 means "batch n-2 has left"
+                if (h0 < h1)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g_al + h0),
+                                 "r"(k2b_smem_addr(outb + h0)), "r"(h1 - h0)
+                                 : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                store_pending = true;
+            }
+        } else {
+            for (uint32_t a = h0 + 16u * tid; a < h1; a += 16u * K2B_THREADS) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(outb + a);
+                pgb_st16(g_al + a, v.x, v.y, v.z, v.w, 1);
+            }
         }
-    } else {
-        for (uint32_t a = h0 + 16u * tid; a < h1; a += 16u * K2B_THREADS) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(outb + a);
-            pgb_st16(g_al + a, v.x, v.y, v.z, v.w, 1);
-        }
+        if (warp == 1) k2b_store_edges(g_al, outb, phase, T, lane);
     }
-    if (warp == 1) k2b_store_edges(g_al, outb, phase, T, lane);
-    // shared memory must stay intact until the bulk store has read it
-    if (p.store_mode == 0 && tid == 0 && h0 < h1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    // shared memory must stay intact until the last bulk stores have read it
+    if (tid == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // -------------------------------------------------------------- synth ------
@@ -550,41 +591,53 @@ static int launch_k2_ipw(const pgb_k2_params &p, cudaStream_t st, int ipw) {
 }
 
 // Batch path (k2_batch.cuh): plan the shared-memory budget; returns false when the lines are too long for it.
-static bool plan_k2_batch(uint32_t K, uint32_t R, bool gather, uint32_t max_prefix_len, int variant, pgb_k2b_params *bp,
-                          uint32_t *smem_bytes) {
+static bool plan_k2_batch(uint32_t K, uint32_t R, bool gather, uint32_t max_prefix_len, uint32_t suffix_len, int variant,
+                          pgb_k2b_params *bp, uint32_t *smem_bytes) {
     const int bsel = (variant >> 20) & 0xF, msel = (variant >> 24) & 0xF;
     const uint64_t max_line = (uint64_t)max_prefix_len + 4ull * K + 1ull;
-    const uint64_t budget = msel ? (uint64_t)msel * 16384ull : 54ull * 1024ull; // default: four CTAs per SM
+    const uint64_t budget = msel ? (uint64_t)msel * 16384ull : 72ull * 1024ull; // default: three CTAs per SM
     const uint64_t rowcap = ((uint64_t)R + 31ull + 15ull) & ~15ull;
+    const uint64_t pcap = ((uint64_t)(max_prefix_len - std::min(max_prefix_len, suffix_len)) + 31ull + 15ull) & ~15ull;
     const uint64_t vcap = gather ? (((uint64_t)(K + 3u) / 4ull + 2ull + 15ull) & ~15ull) : 0ull;
-    const uint64_t per_line = rowcap + vcap + max_line + 20ull;
-    const uint64_t fixed = 16 + 128 + 4 + 128 + 48;
-    if (budget <= fixed + 4 * per_line) return false;
+    const uint64_t per_line = 2 * rowcap + 2 * pcap + vcap + 2 * max_line + 2 * 16ull;
+    const uint64_t fixed = 16 + 128 + 2 * 32 + 128 + 2 * 160;
+    if (budget <= fixed + 2 * per_line) return false;
     uint64_t B = (budget - fixed) / per_line;
     if (B > 32) B = 32;
-    if (bsel) B = std::min<uint64_t>(B, 4ull * bsel);
-    if (B < 4) return false;
+    if (bsel) B = std::min<uint64_t>(B, 2ull * bsel);
+    if (B < 2) return false;
     bp->K = K;
     bp->R = R;
     bp->B = (uint32_t)B;
     bp->rowcap = (uint32_t)rowcap;
+    bp->pcap = (uint32_t)pcap;
     bp->vcap = (uint32_t)vcap;
-    bp->outcap = (uint32_t)((B * max_line + 32ull + 15ull) & ~15ull);
+    bp->outcap = (uint32_t)((B * max_line + 32ull + 127ull) & ~127ull);
     bp->store_mode = (variant >> 28) & 1;
-    *smem_bytes = pgb_k2b_smem_layout(bp->B, bp->rowcap, bp->vcap, bp->outcap, gather).total;
+    *smem_bytes = pgb_k2b_smem_layout(bp->B, bp->rowcap, bp->pcap, bp->vcap, bp->outcap, gather).total;
     return *smem_bytes <= 227u * 1024u;
 }
 
 template <bool GATHER>
-static int launch_k2_batch(const pgb_k2b_params &bp, uint32_t smem_bytes, cudaStream_t st) {
-    const uint64_t blocks = (bp.n_lines + bp.B - 1) / bp.B;
-    if (blocks > 0x7fffffffull) return PGB_E_ARG;
+static int launch_k2_batch(pgb_k2b_params &bp, uint32_t smem_bytes, int variant, cudaStream_t st) {
+    const uint64_t batches = (bp.n_lines + bp.B - 1) / bp.B;
+    if (batches > 0xffffffffull) return PGB_E_ARG;
+    bp.n_batches = (uint32_t)batches;
     cudaError_t e = cudaFuncSetAttribute(k2_batch_kernel<GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) {
-        pgb_set_error("cudaFuncSetAttribute(k2_batch_kernel, %u bytes): %s", smem_bytes, cudaGetErrorString(e));
+    int per_sm = 0, dev = 0, sms = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_batch_kernel<GATHER>, K2B_THREADS, smem_bytes);
+    if (e == cudaSuccess) e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess || per_sm < 1 || sms < 1) {
+        pgb_set_error("k2_batch_kernel launch configuration (%u bytes of shared memory): %s", smem_bytes, cudaGetErrorString(e));
         return PGB_E_CUDA;
     }
-    k2_batch_kernel<GATHER><<<(unsigned)blocks, K2B_THREADS, smem_bytes, st>>>(bp);
+    // persistent grid: every SM full; bits 29-30 of the variant scale it down (A/B runs)
+    uint64_t grid = (uint64_t)per_sm * (uint64_t)sms;
+    const int gsel = (variant >> 29) & 3;
+    if (gsel) grid = std::max<uint64_t>((uint64_t)sms, grid * (4 - gsel) / 4);
+    if (grid > batches) grid = batches;
+    k2_batch_kernel<GATHER><<<(unsigned)grid, K2B_THREADS, smem_bytes, st>>>(bp);
     return check_launch("k2_batch_kernel");
 }
 
@@ -594,9 +647,10 @@ static int launch_k2_batch(const pgb_k2b_params &bp, uint32_t smem_bytes, cudaSt
 //          bits 12-15 tile size = 4 KiB << n (0 => 16 KiB)
 //          bits 16-19 batch path (k2_batch.cuh): 0 => default (gather launches whose batch fits), 1 => off, 2 => on
 //                     whenever the batch fits (also keep-all)
-//          bits 20-23 batch path: lines per CTA <= 4 * n (0 => up to 32)
-//          bits 24-27 batch path: shared-memory budget = n * 16 KiB (0 => 54 KiB, four CTAs per SM)
+//          bits 20-23 batch path: lines per batch <= 2 * n (0 => up to 32)
+//          bits 24-27 batch path: shared-memory budget = n * 16 KiB (0 => 72 KiB, three CTAs per SM)
 //          bit  28    batch path: 16-byte st.global stores instead of the bulk async store
+//          bits 29-30 batch path: persistent grid scaled to (4 - n) / 4 of the resident maximum
 extern "C" int pgb_dev_format_lines_ex(const uint8_t *records, uint32_t record_bytes, const pgb_line_meta *meta,
                                        uint64_t n_lines, const uint8_t *prefix_blob, uint32_t suffix, uint32_t suffix_len,
                                        const uint32_t *kidx, uint32_t n_kept, uint32_t max_prefix_len, uint8_t *out,
@@ -611,7 +665,7 @@ extern "C" int pgb_dev_format_lines_ex(const uint8_t *records, uint32_t record_b
     if (bmode != 1 && (record_bytes || n_kept == 0) && (gatherp || bmode == 2)) {
         pgb_k2b_params bp;
         uint32_t smem_bytes = 0;
-        if (plan_k2_batch(n_kept, record_bytes, gatherp, max_prefix_len, variant, &bp, &smem_bytes)) {
+        if (plan_k2_batch(n_kept, record_bytes, gatherp, max_prefix_len, suffix_len, variant, &bp, &smem_bytes)) {
             bp.records = records;
             bp.meta = meta;
             bp.prefix_blob = prefix_blob;
@@ -621,7 +675,7 @@ extern "C" int pgb_dev_format_lines_ex(const uint8_t *records, uint32_t record_b
             bp.sfx = suffix;
             bp.sfx_len = suffix_len;
             bp.kidx_vec = kidx_vec;
-            return gatherp ? launch_k2_batch<true>(bp, smem_bytes, st) : launch_k2_batch<false>(bp, smem_bytes, st);
+            return gatherp ? launch_k2_batch<true>(bp, smem_bytes, variant, st) : launch_k2_batch<false>(bp, smem_bytes, variant, st);
         }
     }
     pgb_k2_params p;

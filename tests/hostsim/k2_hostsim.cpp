@@ -36,8 +36,10 @@ static uint32_t sim_meta(std::vector<pgb_line_meta> &meta, uint64_t pitch, const
     return maxp;
 }
 
-// The batch path (k2_batch.cuh), phase by phase with a loop over the CTA's threads standing in
-// for each __syncthreads()-delimited phase; bulk copies are memcpy()s.
+// The batch path (k2_batch.cuh): the persistent kernel's loop run for `grid` CTAs one after the other,
+// phase by phase, with a loop over the CTA's threads standing in for each __syncthreads()-delimited
+// phase; bulk copies are memcpy()s (so the two-stage pipeline degenerates to its data flow: the stage
+// indices, tables and images alternate exactly as on the device).
 extern "C" int sim_format_lines_batch(const uint8_t *records, uint64_t pitch, uint32_t R, const uint32_t *var_row,
                                       uint64_t n_lines, const uint8_t *prefix_blob, const uint64_t *prefix_off,
                                       const uint32_t *kidx, uint32_t K, uint8_t *out, uint32_t B, uint32_t sfx,
@@ -52,47 +54,78 @@ extern "C" int sim_format_lines_batch(const uint8_t *records, uint64_t pitch, ui
     p.kidx = kidx;
     p.out = out;
     p.n_lines = n_lines;
+    p.n_batches = (uint32_t)((n_lines + B - 1) / B);
     p.K = K;
     p.R = R;
     p.B = B;
     p.rowcap = pgb_k2b_align(R + 31u, 16);
+    p.pcap = pgb_k2b_align(maxp - (maxp < sfx_len ? maxp : sfx_len) + 31u, 16);
     p.vcap = gather ? pgb_k2b_align((K + 3u) / 4u + 2u, 16) : 0u;
     const uint64_t max_line = (uint64_t)maxp + 4ull * K + 1ull;
-    p.outcap = pgb_k2b_align((uint32_t)(B * max_line + 32u), 16);
+    p.outcap = pgb_k2b_align((uint32_t)(B * max_line + 32u), 128);
     p.sfx = sfx;
     p.sfx_len = sfx_len;
     p.kidx_vec = kidx_vec ? 1u : 0u;
     p.store_mode = 0;
-    const pgb_k2b_layout L = pgb_k2b_smem_layout(p.B, p.rowcap, p.vcap, p.outcap, gather);
+    const pgb_k2b_layout L = pgb_k2b_smem_layout(p.B, p.rowcap, p.pcap, p.vcap, p.outcap, gather);
     std::vector<uint8_t> smem_store(L.total + 256);
     uint8_t *smem = smem_store.data() + ((128 - ((uintptr_t)smem_store.data() & 127)) & 127);
-    for (uint64_t i0 = 0; i0 < n_lines; i0 += B) {
-        memset(smem, 0xCD, L.total); // stale shared memory
-        const uint32_t nbl = (uint32_t)(n_lines - i0 < B ? n_lines - i0 : B);
-        uint32_t span_lo = 0, span_len = K ? R : 0u;
-        if (gather && K) {
-            span_lo = kidx[0] >> 2;
-            span_len = (kidx[K - 1] >> 2) + 1u - span_lo;
-        }
-        for (uint32_t t = 0; t < K2B_THREADS; t++) k2b_build_lut(smem, L, t);
-        for (uint32_t t = 0; t < K2B_THREADS; t++) k2b_phase_meta(p, smem, L, i0, nbl, t, span_lo, span_len);
-        for (uint32_t t = 0; t < K2B_THREADS; t++) k2b_phase_prefix(p, smem, L, nbl, t >> 5, t & 31u);
-        if (gather)
-            for (uint32_t t = 0; t < K2B_THREADS; t++) k2b_phase_compact(p, smem, L, nbl, t, span_lo);
+    uint32_t span_lo = 0, span_len = K ? R : 0u;
+    if (gather && K) {
+        span_lo = kidx[0] >> 2;
+        span_len = (kidx[K - 1] >> 2) + 1u - span_lo;
+    }
+    const uint32_t nb = (K + 3u) >> 2;
+    std::vector<pgb_k2b_plan> plan0(K2B_THREADS);
+    for (uint32_t t = 0; t < K2B_THREADS; t++) {
+        const uint32_t jl = t & (k2b_compact_width(nb) - 1u);
+        plan0[t] = pgb_k2b_plan{{0u, 0u, 0u, 0u}};
+        if (gather && K && nb <= K2B_THREADS && jl < nb) plan0[t] = k2b_load_plan(p, jl, span_lo);
+    }
+    auto lines_of = [&](uint64_t b) -> uint32_t {
+        if (b >= p.n_batches) return 0u;
+        const uint64_t left = n_lines - b * B;
+        return left < B ? (uint32_t)left : B;
+    };
+    auto issue = [&](uint64_t b, uint32_t stage) {
+        const uint32_t nbl = lines_of(b);
+        if (!nbl) return;
         for (uint32_t t = 0; t < K2B_THREADS; t++) {
-            if (gather) k2b_phase_format<true>(p, smem, L, nbl, t >> 5, t & 31u);
-            else k2b_phase_format<false>(p, smem, L, nbl, t >> 5, t & 31u);
+            pgb_line_meta m = {};
+            if (t <= nbl) m = meta[b * B + t];
+            k2b_phase_issue(p, smem, L, stage, nbl, t, m, meta[b * B].line_off, span_lo, span_len);
         }
-        const uint32_t *lo = reinterpret_cast<const uint32_t *>(smem + L.lo);
-        const uint32_t phase = lo[0], T = lo[nbl] - phase;
-        uint64_t base;
-        memcpy(&base, smem + 8, 8);
-        const uint64_t g_al = (uint64_t)(uintptr_t)p.out + base - phase;
-        if (g_al & 15u) return -1;
-        const uint8_t *outb = smem + L.outb;
-        const uint32_t h0 = phase ? 16u : 0u, h1 = (phase + T) & ~15u;
-        if (h0 < h1) memcpy((void *)(uintptr_t)(g_al + h0), outb + h0, h1 - h0); // the bulk store
-        for (uint32_t lane = 0; lane < 32; lane++) k2b_store_edges(g_al, outb, phase, T, lane);
+    };
+    const uint32_t grid = p.n_batches < 3 ? p.n_batches : 3; // a few "CTAs", several batches each
+    for (uint32_t cta = 0; cta < grid; cta++) {
+        memset(smem, 0xCD, L.total); // stale shared memory
+        for (uint32_t t = 0; t < K2B_THREADS; t++) k2b_build_lut(smem, L, t);
+        uint64_t bt = cta;
+        issue(bt, 0);
+        for (uint32_t n = 0;; n++, bt += grid) {
+            const uint32_t stage = n & 1u;
+            const uint32_t nbl = lines_of(bt);
+            if (!nbl) break;
+            const uint8_t *tab = smem + L.tab[stage];
+            const uint32_t *ols = reinterpret_cast<const uint32_t *>(tab + L.t_ols);
+            const uint32_t phase = ols[0], T = ols[nbl] - phase;
+            uint64_t base;
+            memcpy(&base, tab, 8);
+            issue(bt + grid, stage ^ 1u);
+            for (uint32_t t = 0; t < K2B_THREADS; t++) k2b_phase_prefix(p, smem, L, stage, nbl, t >> 5, t & 31u);
+            if (gather)
+                for (uint32_t t = 0; t < K2B_THREADS; t++) k2b_phase_compact(p, smem, L, stage, nbl, t, span_lo, plan0[t]);
+            for (uint32_t t = 0; t < K2B_THREADS; t++) {
+                if (gather) k2b_phase_format<true>(p, smem, L, stage, nbl, t >> 5, t & 31u);
+                else k2b_phase_format<false>(p, smem, L, stage, nbl, t >> 5, t & 31u);
+            }
+            const uint64_t g_al = (uint64_t)(uintptr_t)p.out + base - phase;
+            if (g_al & 15u) return -1;
+            const uint8_t *outb = smem + L.outb[stage];
+            const uint32_t h0 = phase ? 16u : 0u, h1 = (phase + T) & ~15u;
+            if (h0 < h1) memcpy((void *)(uintptr_t)(g_al + h0), outb + h0, h1 - h0); // the bulk store
+            for (uint32_t lane = 0; lane < 32; lane++) k2b_store_edges(g_al, outb, phase, T, lane);
+        }
     }
     return 0;
 }

@@ -114,7 +114,11 @@ def run_sim_batch(k2sim, rng, n, m, k_sel, var_sel, plen, phase, B, sfx=b"", kid
         ki = kstore[s0:s0 + k + 8]
         ki[:k] = sidx
     pre = [bytes(rng.integers(33, 127, size=rng.integers(plen[0], plen[1] + 1), dtype=np.uint8)) for _ in vr]
-    blob = np.frombuffer(b"".join(pre) + b"\0" * 8, dtype=np.uint8).copy()
+    # the batch path fetches the 16-byte blocks around each prefix: keep 16 readable bytes on either side
+    joined = b"".join(pre)
+    bstore = np.zeros(len(joined) + 64, np.uint8)
+    blob = bstore[16 + int(rng.integers(0, 16)):][:len(joined) + 8]
+    blob[:len(joined)] = np.frombuffer(joined, dtype=np.uint8)
     off = np.zeros(len(vr) + 1, np.uint64)
     off[1:] = np.cumsum([len(x) for x in pre])
     exp = onp.format_body(recs, vr, sidx, [x + sfx for x in pre])
@@ -174,7 +178,9 @@ def test_batch_clustered_selection_stages_only_the_span(k2sim):
         sidx = np.sort(rng.choice(np.arange(lo, hi), size=min(hi - lo, 60), replace=False)).astype(np.uint32)
         ki = np.concatenate([sidx, np.zeros(8, np.uint32)]).astype(np.uint32)
         pre = [bytes(rng.integers(33, 127, size=rng.integers(3, 30), dtype=np.uint8)) for _ in range(9)]
-        blob = np.frombuffer(b"".join(pre) + b"\0" * 8, dtype=np.uint8).copy()
+        bstore = np.zeros(sum(len(x) for x in pre) + 64, np.uint8)
+        blob = bstore[16:]
+        blob[:len(b"".join(pre))] = np.frombuffer(b"".join(pre), dtype=np.uint8)
         off = np.zeros(10, np.uint64)
         off[1:] = np.cumsum([len(x) for x in pre])
         exp = onp.format_body(recs, np.arange(9), sidx, pre)
