@@ -179,7 +179,8 @@ typedef struct pgb_line_meta {
     uint64_t rec_off;  /* device record index: byte offset of the variant's record from `records` */
     uint64_t pfx_off;  /* byte offset of the line prefix in prefix_blob                         */
     uint32_t pfx_len;  /* P_v                                                                   */
-    uint32_t reserved;
+    uint32_t reserved; /* bit 0: the launch's prefixes are packed back to back in prefix_blob (K1 sets it
+                          unless it was given explicit prefix lengths); other bits 0                */
 } pgb_line_meta;
 
 /* K0: sample keep-mask (one byte per sample, non-zero = keep) -> ascending kept-index

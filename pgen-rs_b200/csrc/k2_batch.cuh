@@ -33,9 +33,10 @@
 #pragma once
 #include "k2_core.cuh"
 
-#define K2B_THREADS 256
-#define K2B_WARPS 8
-#define K2B_MAX_LINES 128
+#define K2B_THREADS 288 // 8 consumer warps + 1 producer warp
+#define K2B_WARPS 8     // consumer warps
+#define K2B_CONSUMERS 256
+#define K2B_TAB_LINES 128u // a stage table: 8 x 16 bytes of per-warp headers, then 32 bytes per line
 
 struct pgb_k2b_params {
     const uint8_t *records;
@@ -47,23 +48,26 @@ struct pgb_k2b_params {
     uint32_t n_batches;
     uint32_t K;
     uint32_t R;        // record bytes
-    uint32_t B;        // lines per batch, <= K2B_MAX_LINES
+    uint32_t B;        // lines per batch, <= 32 (one producer lane per line)
     uint32_t rowcap;   // shared-memory bytes per staged record: align16(R + 31)
     uint32_t pcap;     // shared-memory bytes per staged prefix: align16(max prefix + 31)
     uint32_t vcap;     // shared-memory bytes per virtual record (gather): align16(ceil(K/4) + 2)
-    uint32_t outcap;   // shared-memory bytes of one output image: align128(B * max_line + 32)
+    uint32_t wcap;     // shared-memory bytes of one consumer warp's part of an output image: align128(LPW * max_line + 32)
+    uint32_t outcap;   // shared-memory bytes of one output image: K2B_WARPS * wcap
     uint32_t sfx;      // bytes appended to every prefix after its blob bytes (little-endian), e.g. "\tGT"
     uint32_t sfx_len;  // 0..4; pfx_len includes it
     uint32_t kidx_vec; // kidx is 16-byte aligned
     uint32_t store_mode; // 0 bulk async store, 1 16-byte st.global by all threads (A/B comparisons)
+    uint32_t images;     // 2: a warp formats batch n+1 while its store of batch n drains; 1: it waits for the drain
+    uint32_t stages;     // input stages (records, prefixes, table): 2 or 3
 };
 
-// Shared memory: [0,8) [8,16) the two stage mbarriers, the text table, then per stage s: a table
-// (body offset of the batch; per line: image offset of the line start and of the GT text, offsets of
-// the staged record span and prefix), the staged records and prefixes; the virtual records; two images.
+// Shared memory: [0,64) the mbarriers (full[s] at 8 s: a stage's copies have landed; empty[s] at 32 + 8 s: the
+// consumer warps are done with a stage), the text table, then per stage s a table (16 bytes per consumer warp: body offset and
+// image byte range of the warp's lines; 32 bytes per line, see k2b_produce), the staged records and prefixes;
+// the gather plan; one virtual record per consumer warp; two images (each one part per consumer warp).
 struct pgb_k2b_layout {
-    uint32_t lut, tab[2], rows[2], pst[2], vrec, outb[2], total;
-    uint32_t t_ols, t_ogs, t_rbase, t_pbase; // offsets inside a stage table
+    uint32_t lut, tab[3], rows[3], pst[3], plan, vrec, outb[2], total;
 };
 
 #if defined(PGB_HOSTSIM)
@@ -75,23 +79,18 @@ struct pgb_k2b_layout {
 PGB_HD uint32_t pgb_k2b_align(uint32_t x, uint32_t a) { return (x + a - 1u) & ~(a - 1u); }
 
 PGB_HD pgb_k2b_layout pgb_k2b_smem_layout(uint32_t B, uint32_t rowcap, uint32_t pcap, uint32_t vcap, uint32_t outcap,
-                                          bool gather) {
+                                          bool gather, uint32_t images = 2, uint32_t stages = 2) {
     pgb_k2b_layout L;
-    L.lut = 16;
-    L.t_ols = 8;
-    L.t_ogs = L.t_ols + 4u * (B + 1u);
-    L.t_rbase = L.t_ogs + 4u * B;
-    L.t_pbase = L.t_rbase + 4u * B;
-    const uint32_t tabsz = pgb_k2b_align(L.t_pbase + 4u * B, 16);
-    L.tab[0] = L.lut + 128;
-    L.tab[1] = L.tab[0] + tabsz;
-    L.rows[0] = L.tab[1] + tabsz;
-    L.rows[1] = L.rows[0] + B * rowcap;
-    L.pst[0] = L.rows[1] + B * rowcap;
-    L.pst[1] = L.pst[0] + B * pcap;
-    L.vrec = L.pst[1] + B * pcap;
-    L.outb[0] = pgb_k2b_align(L.vrec + (gather ? B * vcap : 0u), 128);
-    L.outb[1] = L.outb[0] + outcap;
+    L.lut = 64;
+    const uint32_t tabsz = K2B_TAB_LINES + 32u * B;
+    uint32_t o = L.lut + 128;
+    for (uint32_t s = 0; s < 3; s++) { L.tab[s] = o; if (s < stages) o += tabsz; }
+    for (uint32_t s = 0; s < 3; s++) { L.rows[s] = o; if (s < stages) o += B * rowcap; }
+    for (uint32_t s = 0; s < 3; s++) { L.pst[s] = o; if (s < stages) o += B * pcap; }
+    L.plan = o;
+    L.vrec = L.plan + (gather ? vcap * 16u : 0u); // 16 bytes of plan per virtual-record byte (vcap >= ceil(K/4))
+    L.outb[0] = pgb_k2b_align(L.vrec + (gather ? K2B_WARPS * vcap : 0u), 128);
+    L.outb[1] = images > 1 ? L.outb[0] + outcap : L.outb[0];
     L.total = L.outb[1] + outcap;
     return L;
 }
@@ -110,6 +109,10 @@ PGB_DEV pgb_u2 k2b_lds8(const uint8_t *s) {
     memcpy(&r, s, 8);
     return r;
 }
+PGB_DEV uint32_t pgb_funnel_l(uint32_t lo, uint32_t hi, uint32_t sh) {
+    sh &= 31u;
+    return sh ? ((hi << sh) | (lo >> (32u - sh))) : hi;
+}
 PGB_DEV uint64_t k2b_ld_u64(const uint64_t *p) { return *p; }
 // bulk copies global -> "shared": 16-byte-aligned sources, sizes multiples of 16
 PGB_DEV void k2b_stage_load(uint8_t *, uint8_t *rdst, const uint8_t *rsrc, uint32_t rbytes, uint8_t *pdst,
@@ -127,6 +130,7 @@ PGB_DEV pgb_u2 k2b_lds8(const uint8_t *s) {
     pgb_u2 r = {v.x, v.y};
     return r;
 }
+PGB_DEV uint32_t pgb_funnel_l(uint32_t lo, uint32_t hi, uint32_t sh) { return __funnelshift_l(lo, hi, sh); }
 PGB_DEV uint64_t k2b_ld_u64(const uint64_t *p) { return __ldg(reinterpret_cast<const unsigned long long *>(p)); }
 PGB_DEV uint32_t k2b_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 PGB_DEV void k2b_arrive(uint8_t *mbar) {
@@ -156,115 +160,109 @@ PGB_DEV void k2b_stage_load(uint8_t *mbar, uint8_t *rdst, const uint8_t *rsrc, u
 }
 #endif
 
-// ---- INPUT: stage table + record/prefix fetch of one batch.  Thread t <-> line i0 + t (thread nbl carries
-//      the end of the batch); `m` is that line's pgb_line_meta, `base` the batch's offset in the body.
-//      Threads 0..B-1 each arrive once on the stage's mbarrier. ----
-PGB_DEV void k2b_phase_issue(const pgb_k2b_params &p, uint8_t *smem, const pgb_k2b_layout &L, uint32_t stage, uint32_t nbl,
-                             uint32_t tid, const pgb_line_meta &m, uint64_t base, uint32_t span_lo, uint32_t span_len) {
+// Lines of a batch per consumer warp: warp w formats lines [w * LPW, (w + 1) * LPW) — a contiguous byte range of
+// the output, which the warp stores on its own (no CTA-wide barrier anywhere in the steady state).
+PGB_HD uint32_t k2b_lines_per_warp(uint32_t B) { return (B + K2B_WARPS - 1u) / K2B_WARPS; }
+
+// ---- PRODUCER (one warp): stage table + record/prefix fetch of one batch.  Lane <-> line i0 + lane (B <= 32);
+//      `m` is that line's pgb_line_meta, `first_off` the body offset of the first line of the lane's consumer
+//      warp (a shuffle on the device), `next_off` the body offset of the line after the lane's, `base` / `end_off`
+//      the body offsets of the batch's first line / end, `pfx0` the prefix offset of its first line.  Every lane
+//      arrives once on the stage's `full` barrier (after its table stores: the arrive releases them to the
+//      consumers).  `packed`: K1 marked the prefixes as packed back to back (pgb_line_meta::reserved bit 0), so
+//      the batch's prefixes are one byte range and travel in ONE bulk copy, issued by lane 0.
+//      Table, per consumer warp (16 bytes): body offset of its first line (u64), image offsets of its first byte
+//      and past its last.  Per line (32 bytes): [0] image offset of the line start, [1] prefix bytes to copy,
+//      [2] shared-memory offset of the staged prefix, [3] image offset of the newline, [4] shared-memory offset of
+//      the staged record span, [5] image offset of the GT text, [6]/[7] image offsets of the first / past-the-last
+//      aligned chunk.  Image offsets count from the stage's image; a warp's part starts at w * wcap and keeps the
+//      16-byte phase of the global address it will be stored to. ----
+PGB_DEV void k2b_produce(const pgb_k2b_params &p, uint8_t *smem, const pgb_k2b_layout &L, uint32_t stage, uint32_t nbl,
+                         uint32_t lane, const pgb_line_meta &m, uint64_t first_off, uint64_t next_off, uint64_t base,
+                         uint64_t end_off, uint64_t pfx0, bool packed, uint32_t span_lo, uint32_t span_len) {
     uint8_t *mbar = smem + 8u * stage;
-    if (tid > nbl) {
-        if (tid < p.B) k2b_arrive(mbar);
-        return;
-    }
     uint8_t *tab = smem + L.tab[stage];
-    const uint32_t phase = (uint32_t)((uint64_t)(uintptr_t)p.out + base) & 15u;
-    const uint32_t o_ls = phase + (uint32_t)(m.line_off - base);
-    reinterpret_cast<uint32_t *>(tab + L.t_ols)[tid] = o_ls;
-    if (tid == 0) *reinterpret_cast<uint64_t *>(tab) = base;
-    if (tid == nbl) {
-        if (tid < p.B) k2b_arrive(mbar);
+    const uint8_t *p0 = p.prefix_blob + pfx0;
+    const uint32_t pph0 = (uint32_t)(uintptr_t)p0 & 15u;
+    uint8_t *pdst = nullptr;
+    const uint8_t *psrc = nullptr;
+    uint32_t pbytes = 0;
+    if (lane == 0) {
+        // all prefix bytes of the batch: its size minus the GT text, newlines and suffixes
+        const uint32_t D = (uint32_t)(end_off - base) - nbl * (4u * p.K + 1u + p.sfx_len);
+        if (packed && D) {
+            pdst = smem + L.pst[stage];
+            psrc = p0 - pph0;
+            pbytes = (pph0 + D + 15u) & ~15u;
+        }
+    }
+    const uint32_t LPW = k2b_lines_per_warp(p.B);
+    if (lane < K2B_WARPS && lane * LPW >= nbl) reinterpret_cast<uint32_t *>(tab + 16u * lane)[2] = 0xFFFFFFFFu; // idle warp
+    if (lane >= nbl) {
+        k2b_arrive(mbar);
         return;
     }
-    reinterpret_cast<uint32_t *>(tab + L.t_ogs)[tid] = o_ls + m.pfx_len;
+    const uint32_t w = lane / LPW;
+    const uint32_t phase = (uint32_t)((uint64_t)(uintptr_t)p.out + first_off) & 15u;
+    const uint32_t o_ls = w * p.wcap + phase + (uint32_t)(m.line_off - first_off);
+    if (lane == w * LPW) { // first line of a consumer warp
+        *reinterpret_cast<uint64_t *>(tab + 16u * w) = first_off;
+        reinterpret_cast<uint32_t *>(tab + 16u * w)[2] = o_ls;
+    }
+    if (lane + 1u == nbl || lane + 1u == (w + 1u) * LPW) // its last line
+        reinterpret_cast<uint32_t *>(tab + 16u * w)[3] = o_ls + (uint32_t)(next_off - m.line_off);
+    uint32_t *d = reinterpret_cast<uint32_t *>(tab + K2B_TAB_LINES + 32u * lane);
+    const uint32_t dlen = m.pfx_len - p.sfx_len;
+    const uint32_t o_gs = o_ls + m.pfx_len, o_ge = o_gs + 4u * p.K;
     const uint8_t *src = p.records + m.rec_off + span_lo;
     const uint32_t ph = (uint32_t)(uintptr_t)src & 15u;
-    reinterpret_cast<uint32_t *>(tab + L.t_rbase)[tid] = tid * p.rowcap + ph;
-    const uint32_t dlen = m.pfx_len - p.sfx_len;
-    const uint8_t *psrc = p.prefix_blob + m.pfx_off;
-    const uint32_t pph = dlen ? (uint32_t)(uintptr_t)psrc & 15u : 0u;
-    reinterpret_cast<uint32_t *>(tab + L.t_pbase)[tid] = tid * p.pcap + pph;
-    k2b_stage_load(mbar, smem + L.rows[stage] + tid * p.rowcap, src - ph, span_len ? (ph + span_len + 15u) & ~15u : 0u,
-                   smem + L.pst[stage] + tid * p.pcap, psrc - pph, dlen ? (pph + dlen + 15u) & ~15u : 0u);
-}
-
-// ---- prefixes (pfile.rs:157-161) and newlines (pfile.rs:190) into the image; warp <-> line ----
-PGB_DEV void k2b_phase_prefix(const pgb_k2b_params &p, uint8_t *smem, const pgb_k2b_layout &L, uint32_t stage, uint32_t nbl,
-                              uint32_t warp, uint32_t lane) {
-    const uint8_t *tab = smem + L.tab[stage];
-    const uint32_t *ols = reinterpret_cast<const uint32_t *>(tab + L.t_ols);
-    const uint32_t *ogs = reinterpret_cast<const uint32_t *>(tab + L.t_ogs);
-    const uint32_t *pbase = reinterpret_cast<const uint32_t *>(tab + L.t_pbase);
-    uint8_t *outb = smem + L.outb[stage];
-    for (uint32_t l = warp; l < nbl; l += K2B_WARPS) {
-        const uint32_t o_ls = ols[l], dlen = ogs[l] - o_ls - p.sfx_len;
-        const uint8_t *src = smem + L.pst[stage] + pbase[l];
-        for (uint32_t x = lane; x < dlen; x += 32) outb[o_ls + x] = src[x];
-        if (lane < p.sfx_len) outb[o_ls + dlen + lane] = (uint8_t)(p.sfx >> (8u * lane));
-        if (lane == 31) outb[ols[l + 1] - 1u] = '\n';
-    }
-}
-
-// The gather plan of one thread: the four kept samples of virtual-record byte j as (source byte relative to
-// the staged span) | (left shift bringing the sample's two bits to [6 + 2k, 8 + 2k)) << 24.  Constant for the
-// whole kernel: the kept-sample list is the same for every variant (pfile.rs:128,171).
-struct pgb_k2b_plan {
-    uint32_t e[4];
-};
-
-PGB_DEV pgb_k2b_plan k2b_load_plan(const pgb_k2b_params &p, uint32_t j, uint32_t span_lo) {
-    uint32_t s0, s1, s2, s3;
-    if (p.kidx_vec) {
-        const pgb_u4 v = pgb_ld128(p.kidx + 4u * j); // kidx carries 8 entries of padding
-        s0 = v.x; s1 = v.y; s2 = v.z; s3 = v.w;
+    uint32_t pst_off;
+    if (packed) {
+        pst_off = pph0 + (uint32_t)(m.pfx_off - pfx0);
     } else {
-        s0 = pgb_ld32(p.kidx + 4u * j); s1 = pgb_ld32(p.kidx + 4u * j + 1); s2 = pgb_ld32(p.kidx + 4u * j + 2);
-        s3 = pgb_ld32(p.kidx + 4u * j + 3);
+        const uint8_t *q = p.prefix_blob + m.pfx_off;
+        const uint32_t pph = dlen ? (uint32_t)(uintptr_t)q & 15u : 0u;
+        pst_off = lane * p.pcap + pph;
+        if (dlen) {
+            pdst = smem + L.pst[stage] + lane * p.pcap;
+            psrc = q - pph;
+            pbytes = (pph + dlen + 15u) & ~15u;
+        }
     }
-    if (4u * j + 1u >= p.K) s1 = s0; // fields past K (last byte only): any staged byte will do
-    if (4u * j + 2u >= p.K) s2 = s0;
-    if (4u * j + 3u >= p.K) s3 = s0;
-    pgb_k2b_plan pl;
-    pl.e[0] = ((s0 >> 2) - span_lo) | (6u - (s0 & 3u) * 2u) << 24;
-    pl.e[1] = ((s1 >> 2) - span_lo) | (8u - (s1 & 3u) * 2u) << 24;
-    pl.e[2] = ((s2 >> 2) - span_lo) | (10u - (s2 & 3u) * 2u) << 24;
-    pl.e[3] = ((s3 >> 2) - span_lo) | (12u - (s3 & 3u) * 2u) << 24;
-    return pl;
+    d[0] = o_ls;
+    d[1] = dlen;
+    d[2] = L.pst[stage] + pst_off;
+    d[3] = o_ge;
+    d[4] = L.rows[stage] + lane * p.rowcap + ph;
+    d[5] = o_gs;
+    d[6] = (o_gs + 15u) & ~15u;
+    d[7] = o_ge & ~15u;
+    k2b_stage_load(mbar, smem + L.rows[stage] + lane * p.rowcap, src - ph, span_len ? (ph + span_len + 15u) & ~15u : 0u, pdst,
+                   psrc, pbytes);
 }
 
-PGB_DEV uint32_t k2b_compact_byte(const uint8_t *row, const pgb_k2b_plan &pl) {
-    const uint32_t acc = (((uint32_t)row[pl.e[0] & 0xFFFFFFu] << (pl.e[0] >> 24)) & 0x00C0u) |
-                         (((uint32_t)row[pl.e[1] & 0xFFFFFFu] << (pl.e[1] >> 24)) & 0x0300u) |
-                         (((uint32_t)row[pl.e[2] & 0xFFFFFFu] << (pl.e[2] >> 24)) & 0x0C00u) |
-                         (((uint32_t)row[pl.e[3] & 0xFFFFFFu] << (pl.e[3] >> 24)) & 0x3000u);
-    return acc >> 6;
-}
-
-// Thread <-> byte mapping of the compaction: W threads per line (a power of two >= ceil(K/4), at most the CTA),
-// K2B_THREADS / W lines at a time.
-PGB_DEV uint32_t k2b_compact_width(uint32_t nb) {
-    uint32_t W = 32;
-    while (W < nb && W < K2B_THREADS) W <<= 1;
-    return W;
-}
-
-// ---- GATHER: staged records -> packed virtual records, one thread per output byte.  `plan0` is the plan of
-//      byte (tid & (W-1)) when ceil(K/4) <= K2B_THREADS (the common case: loaded once per kernel). ----
-PGB_DEV void k2b_phase_compact(const pgb_k2b_params &p, uint8_t *smem, const pgb_k2b_layout &L, uint32_t stage, uint32_t nbl,
-                               uint32_t tid, uint32_t span_lo, const pgb_k2b_plan &plan0) {
+// The gather plan of virtual-record byte j: its four kept samples as (source byte relative to the staged span) << 5
+// | (left shift bringing the sample's two bits to [6 + 2k, 8 + 2k)).  The same for every variant (the kept-sample
+// list does not depend on the variant, pfile.rs:128,171): built once per CTA into shared memory.
+PGB_DEV void k2b_build_plan(const pgb_k2b_params &p, uint8_t *smem, const pgb_k2b_layout &L, uint32_t tid, uint32_t span_lo) {
     const uint32_t nb = (p.K + 3u) >> 2;
-    const uint32_t W = k2b_compact_width(nb);
-    const uint32_t LP = K2B_THREADS / W, jl = tid & (W - 1u), l0 = tid / W;
-    const uint32_t *rbase = reinterpret_cast<const uint32_t *>(smem + L.tab[stage] + L.t_rbase);
-    const uint8_t *rows = smem + L.rows[stage];
-    uint8_t *vrec = smem + L.vrec;
-    if (nb <= K2B_THREADS) {
-        if (jl < nb)
-            for (uint32_t l = l0; l < nbl; l += LP) vrec[l * p.vcap + jl] = (uint8_t)k2b_compact_byte(rows + rbase[l], plan0);
-        return;
-    }
-    for (uint32_t j = jl; j < nb; j += W) { // long kept lists: the plan is re-read per byte column
-        const pgb_k2b_plan pl = k2b_load_plan(p, j, span_lo);
-        for (uint32_t l = l0; l < nbl; l += LP) vrec[l * p.vcap + j] = (uint8_t)k2b_compact_byte(rows + rbase[l], pl);
+    uint32_t *plan = reinterpret_cast<uint32_t *>(smem + L.plan);
+    for (uint32_t j = tid; j < nb; j += K2B_CONSUMERS) {
+        uint32_t s0, s1, s2, s3;
+        if (p.kidx_vec) {
+            const pgb_u4 v = pgb_ld128(p.kidx + 4u * j); // kidx carries 8 entries of padding
+            s0 = v.x; s1 = v.y; s2 = v.z; s3 = v.w;
+        } else {
+            s0 = pgb_ld32(p.kidx + 4u * j); s1 = pgb_ld32(p.kidx + 4u * j + 1); s2 = pgb_ld32(p.kidx + 4u * j + 2);
+            s3 = pgb_ld32(p.kidx + 4u * j + 3);
+        }
+        if (4u * j + 1u >= p.K) s1 = s0; // fields past K (last byte only): any staged byte will do
+        if (4u * j + 2u >= p.K) s2 = s0;
+        if (4u * j + 3u >= p.K) s3 = s0;
+        plan[4u * j + 0u] = ((s0 >> 2) - span_lo) << 5 | (6u - (s0 & 3u) * 2u);
+        plan[4u * j + 1u] = ((s1 >> 2) - span_lo) << 5 | (8u - (s1 & 3u) * 2u);
+        plan[4u * j + 2u] = ((s2 >> 2) - span_lo) << 5 | (10u - (s2 & 3u) * 2u);
+        plan[4u * j + 3u] = ((s3 >> 2) - span_lo) << 5 | (12u - (s3 & 3u) * 2u);
     }
 }
 
@@ -275,39 +273,59 @@ PGB_DEV uint32_t k2b_gt_byte(const uint8_t *vrec, const uint8_t *lut, uint32_t g
     return lut[code * 8u + (g & 3u)]; // table entry `code`: the text word of genotype `code` comes first
 }
 
-// ---- FORMAT: GT text of every line into the image; warp <-> line ----
+// ---- CONSUMER, one line, first half (a warp per line, no CTA-wide synchronisation): prefix bytes
+//      (pfile.rs:157-161) and the newline (pfile.rs:190) into the image; GATHER (pfile.rs:171-175): lane <->
+//      bytes lane, lane + 32, ... of the warp's virtual record, 4 LDS.U8 + shift/mask per byte. ----
 template <bool GATHER>
-PGB_DEV void k2b_phase_format(const pgb_k2b_params &p, uint8_t *smem, const pgb_k2b_layout &L, uint32_t stage, uint32_t nbl,
-                              uint32_t warp, uint32_t lane) {
-    const uint8_t *tab = smem + L.tab[stage];
-    const uint32_t *ogs = reinterpret_cast<const uint32_t *>(tab + L.t_ogs);
-    const uint32_t *rbase = reinterpret_cast<const uint32_t *>(tab + L.t_rbase);
-    const uint8_t *lut = smem + L.lut;
-    uint8_t *outb = smem + L.outb[stage];
-    const uint32_t K4 = 4u * p.K;
-    for (uint32_t l = warp; l < nbl; l += K2B_WARPS) {
-        const uint8_t *vrec = GATHER ? smem + L.vrec + l * p.vcap : smem + L.rows[stage] + rbase[l];
-        const uint32_t o_gs = ogs[l], o_ge = o_gs + K4;
-        const uint32_t b0 = (o_gs + 15u) & ~15u, b1 = o_ge & ~15u;
-        if (b0 >= b1) { // no aligned chunk inside the text: byte by byte
-            for (uint32_t g = lane; g < K4; g += 32) outb[o_gs + g] = (uint8_t)k2b_gt_byte(vrec, lut, g);
-            continue;
-        }
-        const uint32_t delta = b0 - o_gs; // (A - o_gs) & 15 for any 16-aligned A
-        const uint32_t r8 = (delta & 3u) * 8u, sh = (delta >> 2) * 2u;
-        const uint8_t *vp = vrec + lane;
-        for (uint32_t A = b0 + 16u * lane; A < b1; A += 512u, vp += 32) {
-            const uint32_t w = pgb_prmt(vp[0], vp[1], 0x1140u) >> sh; // 10 code bits: 5 fields
-            const pgb_u2 e01 = k2b_lds8(lut + ((w & 15u) << 3)), e23 = k2b_lds8(lut + ((w & 0xF0u) >> 1));
-            const uint32_t W4 = pgb_prmt(0x2E313030u, 0x00002F09u, ((w >> 4) & 0x30u) | 0x0504u);
-            k2b_sts16(outb + A, pgb_funnel_r(e01.x, e01.y, r8), pgb_funnel_r(e01.y, e23.x, r8),
-                      pgb_funnel_r(e23.x, e23.y, r8), pgb_funnel_r(e23.y, W4, r8));
-        }
-        // <= 15 bytes of text in front of the first chunk (lanes 0-15) and behind the last one (lanes 16-31)
-        const uint32_t x = lane < 16 ? o_gs + lane : b1 + (lane - 16u);
-        const uint32_t end = lane < 16 ? b0 : o_ge;
-        if (x < end) outb[x] = (uint8_t)k2b_gt_byte(vrec, lut, x - o_gs);
+PGB_DEV void k2b_line_gather(const pgb_k2b_params &p, uint8_t *smem, const pgb_k2b_layout &L, uint32_t stage, uint32_t img,
+                             uint32_t l, uint32_t warp, uint32_t lane) {
+    const pgb_u4 d = pgb_lds4(reinterpret_cast<const pgb_u4 *>(smem + L.tab[stage] + K2B_TAB_LINES + 32u * l));
+    uint8_t *outb = smem + L.outb[img];
+    const uint8_t *src = smem + d.z;
+    for (uint32_t x = lane; x < d.y; x += 32) outb[d.x + x] = src[x];
+    if (lane < p.sfx_len) outb[d.x + d.y + lane] = (uint8_t)(p.sfx >> (8u * lane));
+    if (lane == 31) outb[d.w] = '\n';
+    if (!GATHER) return;
+    const uint8_t *row = smem + reinterpret_cast<const uint32_t *>(smem + L.tab[stage] + K2B_TAB_LINES + 32u * l)[4];
+    const uint32_t nb = (p.K + 3u) >> 2;
+    uint8_t *vrec = smem + L.vrec + warp * p.vcap;
+    const pgb_u4 *plan = reinterpret_cast<const pgb_u4 *>(smem + L.plan);
+    for (uint32_t j = lane; j < nb; j += 32) {
+        const pgb_u4 e = pgb_lds4(plan + j);
+        const uint32_t acc = (pgb_funnel_l(0u, row[e.x >> 5], e.x) & 0x00C0u) | (pgb_funnel_l(0u, row[e.y >> 5], e.y) & 0x0300u) |
+                             (pgb_funnel_l(0u, row[e.z >> 5], e.z) & 0x0C00u) | (pgb_funnel_l(0u, row[e.w >> 5], e.w) & 0x3000u);
+        vrec[j] = (uint8_t)(acc >> 6);
     }
+}
+
+// ---- CONSUMER, one line, second half: FORMAT (pfile.rs:177-188) — the GT text into the image ----
+template <bool GATHER>
+PGB_DEV void k2b_line_format(const pgb_k2b_params &p, uint8_t *smem, const pgb_k2b_layout &L, uint32_t stage, uint32_t img,
+                             uint32_t l, uint32_t warp, uint32_t lane) {
+    const pgb_u4 d = pgb_lds4(reinterpret_cast<const pgb_u4 *>(smem + L.tab[stage] + K2B_TAB_LINES + 16u + 32u * l));
+    const uint8_t *lut = smem + L.lut;
+    uint8_t *outb = smem + L.outb[img];
+    const uint8_t *vrec = GATHER ? smem + L.vrec + warp * p.vcap : smem + d.x;
+    const uint32_t o_gs = d.y, b0 = d.z, b1 = d.w;
+    if (b0 >= b1) { // no aligned chunk inside the text: byte by byte
+        const uint32_t K4 = 4u * p.K;
+        for (uint32_t g = lane; g < K4; g += 32) outb[o_gs + g] = (uint8_t)k2b_gt_byte(vrec, lut, g);
+        return;
+    }
+    const uint32_t delta = b0 - o_gs; // (A - o_gs) & 15 for any 16-aligned A
+    const uint32_t r8 = (delta & 3u) * 8u, sh = (delta >> 2) * 2u;
+    const uint8_t *vp = vrec + lane;
+    for (uint32_t A = b0 + 16u * lane; A < b1; A += 512u, vp += 32) {
+        const uint32_t w = pgb_prmt(vp[0], vp[1], 0x1140u) >> sh; // 10 code bits: 5 fields
+        const pgb_u2 e01 = k2b_lds8(lut + ((w & 15u) << 3)), e23 = k2b_lds8(lut + ((w & 0xF0u) >> 1));
+        const uint32_t W4 = pgb_prmt(0x2E313030u, 0x00002F09u, ((w >> 4) & 0x30u) | 0x0504u);
+        k2b_sts16(outb + A, pgb_funnel_r(e01.x, e01.y, r8), pgb_funnel_r(e01.y, e23.x, r8), pgb_funnel_r(e23.x, e23.y, r8),
+                  pgb_funnel_r(e23.y, W4, r8));
+    }
+    // <= 15 bytes of text in front of the first chunk (lanes 0-15) and behind the last one (lanes 16-31)
+    const uint32_t x = lane < 16 ? o_gs + lane : b1 + (lane - 16u);
+    const uint32_t end = lane < 16 ? b0 : o_gs + 4u * p.K;
+    if (x < end) outb[x] = (uint8_t)k2b_gt_byte(vrec, lut, x - o_gs);
 }
 
 // The 16-entry text table: nibble -> the text words of its two genotypes.
@@ -319,16 +337,16 @@ PGB_DEV void k2b_build_lut(uint8_t *smem, const pgb_k2b_layout &L, uint32_t tid)
     }
 }
 
-// Ragged ends of the batch's byte range in global memory (everything else leaves by bulk store):
-// image bytes [phase, phase + T) <-> global [g_al + phase, ...), g_al 16-byte aligned.  One warp.
-PGB_DEV void k2b_store_edges(uint64_t g_al, const uint8_t *outb, uint32_t phase, uint32_t T, uint32_t lane) {
-    const uint32_t h0 = phase ? 16u : 0u, h1 = (phase + T) & ~15u;
-    if (h0 >= h1) { // no aligned chunk: T < 31
-        const uint32_t x = phase + lane;
-        if (x < phase + T) pgb_st8(g_al + x, outb[x]);
+// Ragged ends of a consumer warp's byte range (everything else leaves by bulk store): image bytes [ws, we) <->
+// global [g_al + ws, g_al + we), g_al + (a multiple of 16) 16-byte aligned.  One warp.
+PGB_DEV void k2b_store_edges(uint64_t g_al, const uint8_t *outb, uint32_t ws, uint32_t we, uint32_t lane) {
+    const uint32_t h0 = (ws + 15u) & ~15u, h1 = we & ~15u;
+    if (h0 >= h1) { // no aligned chunk: fewer than 31 bytes
+        const uint32_t x = ws + lane;
+        if (x < we) pgb_st8(g_al + x, outb[x]);
         return;
     }
-    const uint32_t x = lane < 16 ? phase + lane : h1 + (lane - 16u);
-    const uint32_t end = lane < 16 ? h0 : phase + T;
+    const uint32_t x = lane < 16 ? ws + lane : h1 + (lane - 16u);
+    const uint32_t end = lane < 16 ? h0 : we;
     if (x < end) pgb_st8(g_al + x, outb[x]);
 }

@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(K1_THREADS) k1_emit(const uint32_t *__restrict
             a.z = (uint32_t)ro; a.w = (uint32_t)(ro >> 32);
             const uint64_t pf = po[k] - prefix_base;
             b.x = (uint32_t)pf; b.y = (uint32_t)(pf >> 32);
-            b.z = (uint32_t)P; b.w = 0;
+            b.z = (uint32_t)P;
+            b.w = prefix_len ? 0u : 1u; // bit 0: the prefixes of this launch are packed back to back in prefix_blob
             uint4 *dst = reinterpret_cast<uint4 *>(meta + i);
             dst[0] = a;
             dst[1] = b;
@@ -308,10 +309,13 @@ __global__ void __launch_bounds__(K2_THREADS) k2_format_kernel(const pgb_k2_para
 }
 
 // ------------------------------------------------------------ K2 (batch) ---
-// Short lines: a persistent CTA walks batches of B consecutive lines through two shared-memory
-// stages (k2_batch.cuh): records and prefixes of batch n+1 arrive by bulk async copies while batch
-// n is compacted and formatted into an image of its contiguous output range, and the image of
-// batch n leaves by one bulk async store while batch n+1 is formatted into the other image.
+// Short lines: a persistent, warp-specialised CTA walks batches of B consecutive lines through two
+// shared-memory stages (k2_batch.cuh).  Warp 8 is the producer: it reads the pgb_line_meta of a
+// batch one batch ahead, writes the stage's line table and hands the records and prefixes to the
+// bulk-copy engine (completion on the stage's `full` mbarrier).  Warps 0-7 are consumers: a warp per
+// line, they compact the kept samples, format the text into an image of the batch's contiguous
+// output range and release the stage (`empty` mbarrier); the image leaves by ONE bulk async store
+// that drains while the next batch is formatted into the other image.
 __device__ __forceinline__ void k2b_mbar_wait(uint8_t *mbar, uint32_t parity) {
     const uint32_t bar = k2b_smem_addr(mbar);
     uint32_t done;
@@ -327,96 +331,132 @@ template <bool GATHER>
 __global__ void __launch_bounds__(K2B_THREADS) k2_batch_kernel(const pgb_k2b_params p) {
     extern __shared__ __align__(128) uint8_t k2b_smem[];
     uint8_t *smem = k2b_smem;
-    const pgb_k2b_layout L = pgb_k2b_smem_layout(p.B, p.rowcap, p.pcap, p.vcap, p.outcap, GATHER);
+    const pgb_k2b_layout L = pgb_k2b_smem_layout(p.B, p.rowcap, p.pcap, p.vcap, p.outcap, GATHER, p.images, p.stages);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     // record bytes that hold kept samples: all of the record, or the span of the kept-sample list
     uint32_t span_lo = 0, span_len = p.K ? p.R : 0u;
-    pgb_k2b_plan plan0 = {{0u, 0u, 0u, 0u}};
     if (GATHER && p.K) {
         span_lo = __ldg(p.kidx) >> 2;
         span_len = (__ldg(p.kidx + (p.K - 1u)) >> 2) + 1u - span_lo;
-        const uint32_t nb = (p.K + 3u) >> 2, jl = tid & (k2b_compact_width(nb) - 1u);
-        if (nb <= K2B_THREADS && jl < nb) plan0 = k2b_load_plan(p, jl, span_lo);
+        if (tid < K2B_CONSUMERS) k2b_build_plan(p, smem, L, tid, span_lo);
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k2b_smem_addr(smem)), "r"(p.B) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k2b_smem_addr(smem + 8)), "r"(p.B) : "memory");
+        // full[s] at 8 * s: one arrival per producer lane; empty[s] at 32 + 8 * s: one arrival per consumer warp
+        for (uint32_t st = 0; st < 3; st++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k2b_smem_addr(smem + 8u * st)), "r"(32) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k2b_smem_addr(smem + 32u + 8u * st)), "r"(K2B_WARPS)
+                         : "memory");
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     k2b_build_lut(smem, L, tid);
+    __syncthreads(); // barriers initialised, tables built; from here on the two roles never meet at a CTA barrier
 
-    // batches of this CTA: bt, bt + gridDim.x, ...; line range of batch b: [b * B, min(n_lines, (b+1) * B))
-    auto lines_of = [&](uint64_t b) -> uint32_t {
+    // batches of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...; lines of batch b: [b * B, min(n_lines, (b+1) * B))
+    const uint32_t n_lines = (uint32_t)p.n_lines; // < 2^32 (checked by the launcher)
+    auto lines_of = [&](uint32_t b) -> uint32_t {
         if (b >= p.n_batches) return 0u;
-        const uint64_t left = p.n_lines - b * p.B;
-        return left < p.B ? (uint32_t)left : p.B;
+        const uint32_t left = n_lines - b * p.B;
+        return left < p.B ? left : p.B;
     };
-    // the pgb_line_meta of this thread's line in a batch (thread nbl: the end of the batch) and the batch's body offset
-    pgb_line_meta m_next;
-    uint64_t base_next = 0;
-    auto fetch_meta = [&](uint64_t b) {
-        const uint32_t nbl = lines_of(b);
-        if (nbl && tid <= nbl) {
-            m_next = pgb_ld_meta(p.meta + b * p.B + tid);
-            base_next = k2b_ld_u64(&p.meta[b * p.B].line_off);
+    const uint32_t LPW = k2b_lines_per_warp(p.B);
+    if (warp == K2B_WARPS) {
+        // ------------------------------------------------ producer warp ----
+        // The pgb_line_meta of the lane's line in the NEXT batch is kept as loaded: unpacking it right away
+        // would make the warp wait for the load a batch early.
+        uint4 ra = make_uint4(0, 0, 0, 0), rb = ra, first = ra;
+        uint64_t base = 0, end_off = 0;
+        auto fetch_meta = [&](uint32_t b) {
+            const uint32_t nbl = lines_of(b);
+            if (!nbl) return;
+            const pgb_line_meta *m0 = p.meta + (uint64_t)b * p.B;
+            if (lane < nbl) {
+                const uint4 *q = reinterpret_cast<const uint4 *>(m0 + lane);
+                ra = __ldg(q);
+                rb = __ldg(q + 1);
+            }
+            base = k2b_ld_u64(&m0->line_off);
+            end_off = k2b_ld_u64(&m0[nbl].line_off);
+            first = __ldg(reinterpret_cast<const uint4 *>(m0) + 1); // pfx_off, pfx_len, reserved of the first line
+        };
+        uint32_t bt = blockIdx.x;
+        fetch_meta(bt);
+        for (uint32_t stage = 0, par = 0;; bt += gridDim.x) { // par: parity of the stage's current use
+            const uint32_t nbl = lines_of(bt);
+            if (!nbl) break;
+            pgb_line_meta m;
+            m.line_off = ((uint64_t)ra.y << 32) | ra.x;
+            m.rec_off = ((uint64_t)ra.w << 32) | ra.z;
+            m.pfx_off = ((uint64_t)rb.y << 32) | rb.x;
+            m.pfx_len = rb.z;
+            m.reserved = rb.w;
+            const uint64_t base_n = base, end_n = end_off, pfx0_n = ((uint64_t)first.y << 32) | first.x;
+            const bool packed_n = (first.w & 1u) != 0;
+            // body offsets of the first line of the lane's consumer warp and of the line after the lane's
+            const uint32_t fl = lane / LPW * LPW;
+            const uint64_t first_off = ((uint64_t)__shfl_sync(0xffffffffu, ra.y, fl) << 32) | __shfl_sync(0xffffffffu, ra.x, fl);
+            uint64_t next_off = ((uint64_t)__shfl_down_sync(0xffffffffu, ra.y, 1) << 32) | __shfl_down_sync(0xffffffffu, ra.x, 1);
+            if (lane + 1u >= nbl) next_off = end_n;
+            fetch_meta(bt + gridDim.x); // the index read of the batch after this one
+            k2b_mbar_wait(smem + 32u + 8u * stage, par ^ 1u); // consumers are done with the stage
+            k2b_produce(p, smem, L, stage, nbl, lane, m, first_off, next_off, base_n, end_n, pfx0_n, packed_n, span_lo, span_len);
+            if (++stage == p.stages) { stage = 0; par ^= 1u; }
         }
-    };
-    uint64_t bt = blockIdx.x;
-    fetch_meta(bt);
-    __syncthreads(); // mbarriers initialised, table built
-    {
-        const uint32_t nbl = lines_of(bt);
-        if (nbl) k2b_phase_issue(p, smem, L, 0, nbl, tid, m_next, base_next, span_lo, span_len);
+        return;
     }
-    fetch_meta(bt + gridDim.x);
-    bool store_pending = false; // thread 0: a bulk store group is in flight
-    for (uint32_t n = 0;; n++, bt += gridDim.x) {
-        const uint32_t stage = n & 1u;
+    // ---------------------------------------------------- consumer warps ----
+    // Warp w formats lines [w * LPW, (w + 1) * LPW) of every batch into its own part of the image and stores that
+    // contiguous byte range itself: the consumer warps never wait for one another.
+    uint32_t bt = blockIdx.x;
+    for (uint32_t n = 0, stage = 0, par = 0;; n++, bt += gridDim.x) {
         const uint32_t nbl = lines_of(bt);
         if (!nbl) break;
-        // the image about to be rewritten (batch n-2's) must have left shared memory
-        if (tid == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        __syncthreads(); // tables of this stage visible; the other stage's buffers are free
-        {   // INPUT of the next batch, then the index read of the one after
-            const uint32_t nbl1 = lines_of(bt + gridDim.x);
-            if (nbl1) k2b_phase_issue(p, smem, L, stage ^ 1u, nbl1, tid, m_next, base_next, span_lo, span_len);
-            fetch_meta(bt + 2ull * gridDim.x);
+        const uint32_t img = p.images > 1 ? n & 1u : 0u;
+        // the part of the image this warp is about to rewrite (batch n-2's, or n-1's with a single image) must have
+        // left shared memory
+        if (lane == 0) {
+            if (p.images > 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
-        const uint8_t *tab = smem + L.tab[stage];
-        const uint32_t *ols = reinterpret_cast<const uint32_t *>(tab + L.t_ols);
-        const uint32_t phase = ols[0], T = ols[nbl] - phase;
-        const uint64_t g_al = (uint64_t)(uintptr_t)p.out + *reinterpret_cast<const uint64_t *>(tab) - phase;
-        k2b_mbar_wait(smem + 8u * stage, (n >> 1) & 1u);
-        k2b_phase_prefix(p, smem, L, stage, nbl, warp, lane);
-        if (GATHER) {
-            k2b_phase_compact(p, smem, L, stage, nbl, tid, span_lo, plan0);
-            __syncthreads();
+        k2b_mbar_wait(smem + 8u * stage, par); // table written, records and prefixes landed
+        const pgb_u4 h = pgb_lds4(reinterpret_cast<const pgb_u4 *>(smem + L.tab[stage] + 16u * warp));
+        __syncwarp();
+        const uint32_t l1 = (warp + 1u) * LPW < nbl ? (warp + 1u) * LPW : nbl;
+        for (uint32_t l = warp * LPW; l < l1; l++) {
+            k2b_line_gather<GATHER>(p, smem, L, stage, img, l, warp, lane);
+            if (GATHER) __syncwarp();
+            k2b_line_format<GATHER>(p, smem, L, stage, img, l, warp, lane);
+            if (GATHER) __syncwarp();
         }
-        k2b_phase_format<GATHER>(p, smem, L, stage, nbl, warp, lane);
         // the image was written through the generic proxy; the bulk store reads it through the async proxy
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        const uint8_t *outb = smem + L.outb[stage];
-        const uint32_t h0 = phase ? 16u : 0u, h1 = (phase + T) & ~15u;
-        if (p.store_mode == 0) {
-            if (tid == 0) { // one group per batch (possibly empty), so that wait_group.read 1 means "batch n-2 has left"
-                if (h0 < h1)
+        __syncwarp();
+        // this warp no longer reads the stage's table, records or prefixes: let the producer refill it
+        if (lane == 0) k2b_arrive(smem + 32u + 8u * stage);
+        if (++stage == p.stages) { stage = 0; par ^= 1u; }
+        const uint32_t ws = h.z, we = h.w;
+        const uint8_t *outb = smem + L.outb[img];
+        const uint64_t g_al = (uint64_t)(uintptr_t)p.out + (((uint64_t)h.y << 32) | h.x) - ws;
+        if (ws != 0xFFFFFFFFu) {
+            const uint32_t h0 = (ws + 15u) & ~15u, h1 = we & ~15u;
+            if (p.store_mode == 0) {
+                if (lane == 0 && h0 < h1)
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g_al + h0),
                                  "r"(k2b_smem_addr(outb + h0)), "r"(h1 - h0)
                                  : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                store_pending = true;
+            } else {
+                for (uint32_t a = h0 + 16u * lane; a < h1; a += 512u) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(outb + a);
+                    pgb_st16(g_al + a, v.x, v.y, v.z, v.w, 1);
+                }
             }
-        } else {
-            for (uint32_t a = h0 + 16u * tid; a < h1; a += 16u * K2B_THREADS) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(outb + a);
-                pgb_st16(g_al + a, v.x, v.y, v.z, v.w, 1);
-            }
+            k2b_store_edges(g_al, outb, ws, we, lane);
         }
-        if (warp == 1) k2b_store_edges(g_al, outb, phase, T, lane);
+        // one group per batch (possibly empty), so that wait_group.read 1 means "batch n-2 has left"
+        if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     // shared memory must stay intact until the last bulk stores have read it
-    if (tid == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // -------------------------------------------------------------- synth ------
@@ -599,11 +639,15 @@ static bool plan_k2_batch(uint32_t K, uint32_t R, bool gather, uint32_t max_pref
     const uint64_t rowcap = ((uint64_t)R + 31ull + 15ull) & ~15ull;
     const uint64_t pcap = ((uint64_t)(max_prefix_len - std::min(max_prefix_len, suffix_len)) + 31ull + 15ull) & ~15ull;
     const uint64_t vcap = gather ? (((uint64_t)(K + 3u) / 4ull + 2ull + 15ull) & ~15ull) : 0ull;
-    const uint64_t per_line = 2 * rowcap + 2 * pcap + vcap + 2 * max_line + 2 * 16ull;
-    const uint64_t fixed = 16 + 128 + 2 * 32 + 128 + 2 * 160;
+    // measured on the gather-heavy chr22 shape (profiles/README.md): one image per warp and two input stages with
+    // 24 lines per batch beat two images / three stages with the 16 lines those leave room for
+    const uint64_t images = ((variant >> 29) & 1) ? 2 : 1, stages = ((variant >> 30) & 1) ? 3 : 2;
+    const uint64_t per_line = stages * (rowcap + pcap + 32ull) + images * max_line;
+    const uint64_t fixed = 64 + 128 + stages * 128 + 128 + images * K2B_WARPS * 160 + vcap * 16 + vcap * K2B_WARPS;
     if (budget <= fixed + 2 * per_line) return false;
     uint64_t B = (budget - fixed) / per_line;
     if (B > 32) B = 32;
+    if (B > 8) B &= ~7ull; // the same number of lines for each of the eight consumer warps
     if (bsel) B = std::min<uint64_t>(B, 2ull * bsel);
     if (B < 2) return false;
     bp->K = K;
@@ -612,16 +656,19 @@ static bool plan_k2_batch(uint32_t K, uint32_t R, bool gather, uint32_t max_pref
     bp->rowcap = (uint32_t)rowcap;
     bp->pcap = (uint32_t)pcap;
     bp->vcap = (uint32_t)vcap;
-    bp->outcap = (uint32_t)((B * max_line + 32ull + 127ull) & ~127ull);
+    bp->wcap = (uint32_t)((k2b_lines_per_warp((uint32_t)B) * max_line + 32ull + 127ull) & ~127ull);
+    bp->outcap = K2B_WARPS * bp->wcap;
     bp->store_mode = (variant >> 28) & 1;
-    *smem_bytes = pgb_k2b_smem_layout(bp->B, bp->rowcap, bp->pcap, bp->vcap, bp->outcap, gather).total;
+    bp->images = (uint32_t)images;
+    bp->stages = (uint32_t)stages;
+    *smem_bytes = pgb_k2b_smem_layout(bp->B, bp->rowcap, bp->pcap, bp->vcap, bp->outcap, gather, bp->images, bp->stages).total;
     return *smem_bytes <= 227u * 1024u;
 }
 
 template <bool GATHER>
 static int launch_k2_batch(pgb_k2b_params &bp, uint32_t smem_bytes, int variant, cudaStream_t st) {
     const uint64_t batches = (bp.n_lines + bp.B - 1) / bp.B;
-    if (batches > 0xffffffffull) return PGB_E_ARG;
+    if (bp.n_lines > 0xffffffffull) return PGB_E_ARG;
     bp.n_batches = (uint32_t)batches;
     cudaError_t e = cudaFuncSetAttribute(k2_batch_kernel<GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     int per_sm = 0, dev = 0, sms = 0;
@@ -632,10 +679,8 @@ static int launch_k2_batch(pgb_k2b_params &bp, uint32_t smem_bytes, int variant,
         pgb_set_error("k2_batch_kernel launch configuration (%u bytes of shared memory): %s", smem_bytes, cudaGetErrorString(e));
         return PGB_E_CUDA;
     }
-    // persistent grid: every SM full; bits 29-30 of the variant scale it down (A/B runs)
-    uint64_t grid = (uint64_t)per_sm * (uint64_t)sms;
-    const int gsel = (variant >> 29) & 3;
-    if (gsel) grid = std::max<uint64_t>((uint64_t)sms, grid * (4 - gsel) / 4);
+    const uint64_t grid0 = (uint64_t)per_sm * (uint64_t)sms; // persistent grid: every SM full
+    uint64_t grid = grid0;
     if (grid > batches) grid = batches;
     k2_batch_kernel<GATHER><<<(unsigned)grid, K2B_THREADS, smem_bytes, st>>>(bp);
     return check_launch("k2_batch_kernel");
@@ -650,7 +695,8 @@ static int launch_k2_batch(pgb_k2b_params &bp, uint32_t smem_bytes, int variant,
 //          bits 20-23 batch path: lines per batch <= 2 * n (0 => up to 32)
 //          bits 24-27 batch path: shared-memory budget = n * 16 KiB (0 => 72 KiB, three CTAs per SM)
 //          bit  28    batch path: 16-byte st.global stores instead of the bulk async store
-//          bits 29-30 batch path: persistent grid scaled to (4 - n) / 4 of the resident maximum
+//          bit  29    batch path: two output images per warp instead of one
+//          bit  30    batch path: three input stages instead of two
 extern "C" int pgb_dev_format_lines_ex(const uint8_t *records, uint32_t record_bytes, const pgb_line_meta *meta,
                                        uint64_t n_lines, const uint8_t *prefix_blob, uint32_t suffix, uint32_t suffix_len,
                                        const uint32_t *kidx, uint32_t n_kept, uint32_t max_prefix_len, uint8_t *out,
@@ -662,7 +708,11 @@ extern "C" int pgb_dev_format_lines_ex(const uint8_t *records, uint32_t record_b
     const uint32_t kidx_vec = kidx && ((uintptr_t)kidx & 15u) == 0 ? 1u : 0u;
     if (!gatherp) record_bytes = (n_kept + 3u) / 4u; // keep-all: n_kept is the file's sample count
     const int bmode = (variant >> 16) & 0xF;
-    if (bmode != 1 && (record_bytes || n_kept == 0) && (gatherp || bmode == 2)) {
+    // Default use of the batch path (measured, profiles/README.md): every gather launch whose batch fits in shared
+    // memory, and keep-all launches with lines of at most 3 KiB (300 samples: 0.065 vs 0.079 ms; 600: 0.49 vs 0.53 ms;
+    // 1 000 samples, 4 KiB lines: 0.82 vs 0.71 ms — the per-line kernels win from there on).
+    const uint64_t max_line_b = (uint64_t)max_prefix_len + 4ull * n_kept + 1ull;
+    if (bmode != 1 && (record_bytes || n_kept == 0) && (gatherp || max_line_b <= 3072 || bmode == 2)) {
         pgb_k2b_params bp;
         uint32_t smem_bytes = 0;
         if (plan_k2_batch(n_kept, record_bytes, gatherp, max_prefix_len, suffix_len, variant, &bp, &smem_bytes)) {

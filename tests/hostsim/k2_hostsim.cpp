@@ -19,7 +19,7 @@ extern "C" int sim_format_lines_sfx(const uint8_t *records, uint64_t pitch, cons
 // What K1 computes.  sfx_len > 0: the last sfx_len bytes of every prefix are the constant suffix `sfx`
 // and prefix_blob holds only the bytes in front of it (prefix_off[i+1] - prefix_off[i] of them).
 static uint32_t sim_meta(std::vector<pgb_line_meta> &meta, uint64_t pitch, const uint32_t *var_row, uint64_t n_lines,
-                         const uint64_t *prefix_off, uint32_t K, uint32_t sfx_len) {
+                         const uint64_t *prefix_off, uint32_t K, uint32_t sfx_len, uint32_t packed = 1) {
     uint64_t off = 0;
     uint32_t maxp = 0;
     for (uint64_t i = 0; i < n_lines; i++) {
@@ -28,7 +28,7 @@ static uint32_t sim_meta(std::vector<pgb_line_meta> &meta, uint64_t pitch, const
         meta[i].rec_off = (var_row ? var_row[i] : i) * pitch;
         meta[i].pfx_off = prefix_off[i] - prefix_off[0];
         meta[i].pfx_len = (uint32_t)P;
-        meta[i].reserved = 0;
+        meta[i].reserved = packed;
         if (P > maxp) maxp = (uint32_t)P;
         off += P + 4ull * K + 1;
     }
@@ -43,9 +43,10 @@ static uint32_t sim_meta(std::vector<pgb_line_meta> &meta, uint64_t pitch, const
 extern "C" int sim_format_lines_batch(const uint8_t *records, uint64_t pitch, uint32_t R, const uint32_t *var_row,
                                       uint64_t n_lines, const uint8_t *prefix_blob, const uint64_t *prefix_off,
                                       const uint32_t *kidx, uint32_t K, uint8_t *out, uint32_t B, uint32_t sfx,
-                                      uint32_t sfx_len, int kidx_vec) {
+                                      uint32_t sfx_len, int flags) {
+    // flags: bit 0 kidx_vec, bit 1 prefixes NOT marked as packed (one bulk copy per line instead of per batch)
     std::vector<pgb_line_meta> meta(n_lines + 1);
-    const uint32_t maxp = sim_meta(meta, pitch, var_row, n_lines, prefix_off, K, sfx_len);
+    const uint32_t maxp = sim_meta(meta, pitch, var_row, n_lines, prefix_off, K, sfx_len, (flags & 2) ? 0u : 1u);
     const bool gather = kidx != nullptr;
     pgb_k2b_params p;
     p.records = records;
@@ -62,12 +63,15 @@ extern "C" int sim_format_lines_batch(const uint8_t *records, uint64_t pitch, ui
     p.pcap = pgb_k2b_align(maxp - (maxp < sfx_len ? maxp : sfx_len) + 31u, 16);
     p.vcap = gather ? pgb_k2b_align((K + 3u) / 4u + 2u, 16) : 0u;
     const uint64_t max_line = (uint64_t)maxp + 4ull * K + 1ull;
-    p.outcap = pgb_k2b_align((uint32_t)(B * max_line + 32u), 128);
+    p.wcap = pgb_k2b_align((uint32_t)(k2b_lines_per_warp(B) * max_line + 32u), 128);
+    p.outcap = K2B_WARPS * p.wcap;
     p.sfx = sfx;
     p.sfx_len = sfx_len;
-    p.kidx_vec = kidx_vec ? 1u : 0u;
+    p.kidx_vec = (flags & 1) ? 1u : 0u;
     p.store_mode = 0;
-    const pgb_k2b_layout L = pgb_k2b_smem_layout(p.B, p.rowcap, p.pcap, p.vcap, p.outcap, gather);
+    p.images = (flags & 4) ? 1u : 2u;
+    p.stages = (flags & 8) ? 3u : 2u;
+    const pgb_k2b_layout L = pgb_k2b_smem_layout(p.B, p.rowcap, p.pcap, p.vcap, p.outcap, gather, p.images, p.stages);
     std::vector<uint8_t> smem_store(L.total + 256);
     uint8_t *smem = smem_store.data() + ((128 - ((uintptr_t)smem_store.data() & 127)) & 127);
     uint32_t span_lo = 0, span_len = K ? R : 0u;
@@ -75,56 +79,64 @@ extern "C" int sim_format_lines_batch(const uint8_t *records, uint64_t pitch, ui
         span_lo = kidx[0] >> 2;
         span_len = (kidx[K - 1] >> 2) + 1u - span_lo;
     }
-    const uint32_t nb = (K + 3u) >> 2;
-    std::vector<pgb_k2b_plan> plan0(K2B_THREADS);
-    for (uint32_t t = 0; t < K2B_THREADS; t++) {
-        const uint32_t jl = t & (k2b_compact_width(nb) - 1u);
-        plan0[t] = pgb_k2b_plan{{0u, 0u, 0u, 0u}};
-        if (gather && K && nb <= K2B_THREADS && jl < nb) plan0[t] = k2b_load_plan(p, jl, span_lo);
-    }
     auto lines_of = [&](uint64_t b) -> uint32_t {
         if (b >= p.n_batches) return 0u;
         const uint64_t left = n_lines - b * B;
         return left < B ? (uint32_t)left : B;
     };
-    auto issue = [&](uint64_t b, uint32_t stage) {
+    const uint32_t LPW = k2b_lines_per_warp(B);
+    auto issue = [&](uint64_t b, uint32_t stage) { // the producer warp
         const uint32_t nbl = lines_of(b);
         if (!nbl) return;
-        for (uint32_t t = 0; t < K2B_THREADS; t++) {
+        for (uint32_t lane = 0; lane < 32; lane++) {
             pgb_line_meta m = {};
-            if (t <= nbl) m = meta[b * B + t];
-            k2b_phase_issue(p, smem, L, stage, nbl, t, m, meta[b * B].line_off, span_lo, span_len);
+            uint64_t first_off = 0, next_off = 0;
+            if (lane < nbl) {
+                m = meta[b * B + lane];
+                first_off = meta[b * B + lane / LPW * LPW].line_off;
+                next_off = meta[b * B + lane + 1].line_off;
+            }
+            k2b_produce(p, smem, L, stage, nbl, lane, m, first_off, next_off, meta[b * B].line_off, meta[b * B + nbl].line_off,
+                        meta[b * B].pfx_off, (meta[b * B].reserved & 1u) != 0, span_lo, span_len);
         }
     };
     const uint32_t grid = p.n_batches < 3 ? p.n_batches : 3; // a few "CTAs", several batches each
     for (uint32_t cta = 0; cta < grid; cta++) {
         memset(smem, 0xCD, L.total); // stale shared memory
         for (uint32_t t = 0; t < K2B_THREADS; t++) k2b_build_lut(smem, L, t);
+        if (gather && K)
+            for (uint32_t t = 0; t < K2B_CONSUMERS; t++) k2b_build_plan(p, smem, L, t, span_lo);
         uint64_t bt = cta;
-        issue(bt, 0);
+        for (uint32_t s = 0; s + 1 < p.stages; s++) issue(bt + (uint64_t)s * grid, s); // the producer runs ahead
         for (uint32_t n = 0;; n++, bt += grid) {
-            const uint32_t stage = n & 1u;
+            const uint32_t stage = n % p.stages, img = p.images > 1 ? n & 1u : 0u;
             const uint32_t nbl = lines_of(bt);
             if (!nbl) break;
-            const uint8_t *tab = smem + L.tab[stage];
-            const uint32_t *ols = reinterpret_cast<const uint32_t *>(tab + L.t_ols);
-            const uint32_t phase = ols[0], T = ols[nbl] - phase;
-            uint64_t base;
-            memcpy(&base, tab, 8);
-            issue(bt + grid, stage ^ 1u);
-            for (uint32_t t = 0; t < K2B_THREADS; t++) k2b_phase_prefix(p, smem, L, stage, nbl, t >> 5, t & 31u);
-            if (gather)
-                for (uint32_t t = 0; t < K2B_THREADS; t++) k2b_phase_compact(p, smem, L, stage, nbl, t, span_lo, plan0[t]);
-            for (uint32_t t = 0; t < K2B_THREADS; t++) {
-                if (gather) k2b_phase_format<true>(p, smem, L, stage, nbl, t >> 5, t & 31u);
-                else k2b_phase_format<false>(p, smem, L, stage, nbl, t >> 5, t & 31u);
+            issue(bt + (uint64_t)(p.stages - 1) * grid, (n + p.stages - 1) % p.stages);
+            for (uint32_t warp = 0; warp < K2B_WARPS; warp++) {
+                uint32_t h[4];
+                memcpy(h, smem + L.tab[stage] + 16u * warp, 16);
+                const uint32_t l1 = (warp + 1u) * LPW < nbl ? (warp + 1u) * LPW : nbl;
+                for (uint32_t l = warp * LPW; l < l1; l++) {
+                    for (uint32_t lane = 0; lane < 32; lane++) {
+                        if (gather) k2b_line_gather<true>(p, smem, L, stage, img, l, warp, lane);
+                        else k2b_line_gather<false>(p, smem, L, stage, img, l, warp, lane);
+                    }
+                    for (uint32_t lane = 0; lane < 32; lane++) {
+                        if (gather) k2b_line_format<true>(p, smem, L, stage, img, l, warp, lane);
+                        else k2b_line_format<false>(p, smem, L, stage, img, l, warp, lane);
+                    }
+                }
+                const uint32_t ws = h[2], we = h[3];
+                if ((ws == 0xFFFFFFFFu) != (warp * LPW >= nbl)) return -2;
+                if (ws == 0xFFFFFFFFu) continue;
+                const uint64_t g_al = (uint64_t)(uintptr_t)p.out + (((uint64_t)h[1] << 32) | h[0]) - ws;
+                if (g_al & 15u) return -1;
+                const uint8_t *outb = smem + L.outb[img];
+                const uint32_t h0 = (ws + 15u) & ~15u, h1 = we & ~15u;
+                if (h0 < h1) memcpy((void *)(uintptr_t)(g_al + h0), outb + h0, h1 - h0); // the warp's bulk store
+                for (uint32_t lane = 0; lane < 32; lane++) k2b_store_edges(g_al, outb, ws, we, lane);
             }
-            const uint64_t g_al = (uint64_t)(uintptr_t)p.out + base - phase;
-            if (g_al & 15u) return -1;
-            const uint8_t *outb = smem + L.outb[stage];
-            const uint32_t h0 = phase ? 16u : 0u, h1 = (phase + T) & ~15u;
-            if (h0 < h1) memcpy((void *)(uintptr_t)(g_al + h0), outb + h0, h1 - h0); // the bulk store
-            for (uint32_t lane = 0; lane < 32; lane++) k2b_store_edges(g_al, outb, phase, T, lane);
         }
     }
     return 0;

@@ -90,7 +90,8 @@ def test_prefix_longer_than_a_tile(k2sim):
 
 # ---- batch path (k2_batch.cuh) and the constant prefix suffix ("\tGT" appended on the device) ----
 
-def run_sim_batch(k2sim, rng, n, m, k_sel, var_sel, plen, phase, B, sfx=b"", kidx_vec=1, per_line=False, variant=0):
+def run_sim_batch(k2sim, rng, n, m, k_sel, var_sel, plen, phase, B, sfx=b"", kidx_vec=1, per_line=False, variant=0,
+                  unpacked=0):
     """per_line=True runs the per-line kernels (k2_core.cuh) with the suffix instead of the batch path."""
     r = synth.record_size(n)
     recs = rng.integers(0, 256, size=(m, r), dtype=np.uint8)
@@ -133,7 +134,7 @@ def run_sim_batch(k2sim, rng, n, m, k_sel, var_sel, plen, phase, B, sfx=b"", kid
     else:
         rc = k2sim.sim_format_lines_batch(flat.ctypes.data, r, r, vptr, len(vr), blob.ctypes.data, off.ctypes.data,
                                           None if ki is None else ki.ctypes.data, k, buf.ctypes.data + start, B,
-                                          sfx_word, len(sfx), kidx_vec)
+                                          sfx_word, len(sfx), kidx_vec | (2 if unpacked else 0) | (4 if phase % 3 == 0 else 0) | (8 if phase % 5 < 2 else 0))
     assert rc == 0
     got = buf[start:start + len(exp)].tobytes()
     if got != exp:
@@ -165,7 +166,7 @@ def test_batch_random_shapes(k2sim):
         plen = [(0, 0), (0, 5), (1, 40), (30, 200), (60, 70), (150, 400)][rng.integers(0, 6)]
         sfx = [b"", b"\tGT", b"x", b"abcd"][rng.integers(0, 4)]
         run_sim_batch(k2sim, rng, n, m, k_sel, var_sel, plen, int(rng.integers(0, 512)), int(rng.integers(1, 33)), sfx,
-                      kidx_vec=int(rng.integers(0, 2)))
+                      kidx_vec=int(rng.integers(0, 2)), unpacked=int(rng.integers(0, 2)))
 
 
 def test_batch_clustered_selection_stages_only_the_span(k2sim):
