@@ -22,6 +22,12 @@ Multi-GPU (torchrun): rank r owns the contiguous variant range [r*M, (r+1)*M) of
 (N_gpus*M)-variant matrix — weak scaling, no data-path collective (NCCL only for the timing
 barrier and the max-over-ranks reduction).
 
+Every line also carries `config5`: BASELINE.json configs[4] (500 000 samples x 200 000 variants, 400 GB of
+VCF) in STRONG scaling — rank r formats the contiguous variant range [r*200000/N, (r+1)*200000/N), records resident
+in HBM, output ring-buffered — plus one call of the product's own multi-device sharding
+(pgb_export_gt_vcf_mem(devices=[0..N-1]) from rank 0) on a slice of that matrix that crosses the 4 GiB record
+offset, checked bit for bit against the device-resident path.
+
 `--impl reference` times the CPU restatement of Pfile::output_vcf (oracle/pgen_oracle.c in its
 reference-faithful I/O mode: lseek+read per variant, 8 KiB buffered writer, two appends per
 genotype; the Rust binary itself cannot be built in this image) on a bounded sample of the
@@ -252,6 +258,276 @@ def run_reference(args, wl, rank, world):
     print(json.dumps(line), flush=True)
 
 
+
+# ------------------------------------------------- host-side ceilings (measured, per run) ---
+def host_write_probe(h_out_np, n_threads):
+    """CPU threads filling the page-locked output buffer (numpy copies release the GIL): what the host
+    memory system takes when the writers are cores instead of the GPUs' DMA engines."""
+    nbytes = min(h_out_np.nbytes, 4 << 30)
+    per = nbytes // n_threads // 4096 * 4096
+    src = np.full(per, 48, np.uint8)
+
+    def work(i):
+        np.copyto(h_out_np[i * per:(i + 1) * per], src)
+
+    best = 0.0
+    for _ in range(2):
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(i,)) for i in range(n_threads)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        best = max(best, per * n_threads / (time.perf_counter() - t0) / 1e9)
+    return best
+
+
+def d2h_calibration(torch, d_out, h_out, total, barrier):
+    """Device->host ceilings of this rank, all ranks copying at the same time (the host side is shared):
+    (a) ONE copy of the whole body, (b) the export's own pattern without kernels — 128 MiB chunks cycling
+    over three streams.  The e2e roofline peak is the larger of the two."""
+    ca, cb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h_out[:1 << 20].copy_(d_out[:1 << 20], non_blocking=True)
+    barrier()
+    ca.record()
+    h_out[:total].copy_(d_out[:total], non_blocking=True)
+    cb.record()
+    torch.cuda.synchronize()
+    whole = total / (ca.elapsed_time(cb) * 1e-3) / 1e9
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    chunk = 128 << 20
+    barrier()
+    t0 = time.perf_counter()
+    for i, a in enumerate(range(0, total, chunk)):
+        b = min(total, a + chunk)
+        with torch.cuda.stream(streams[i % 3]):
+            h_out[a:b].copy_(d_out[a:b], non_blocking=True)
+    torch.cuda.synchronize()
+    chunked = total / (time.perf_counter() - t0) / 1e9
+    return {"whole_body_gbs": whole, "chunked_3_streams_128MiB_gbs": chunked, "peak": max(whole, chunked)}
+
+
+def file_sink_ceilings(path, mv, n_threads):
+    """Raw rates of the candidate sink strategies on the file system of `path`, for the same bytes the export
+    writes (no GPU involved): n_threads buffered pwrite()s, n_threads O_DIRECT pwrite()s, n_threads copies
+    through a MAP_SHARED mapping, and one buffered pwrite() thread.  No fsync, like the export."""
+    import mmap
+    total = len(mv) // 4096 * 4096
+    per = total // n_threads // 4096 * 4096
+    out = {}
+
+    def run(name, flags, nt, use_map=False):
+        try:
+            fd = os.open(path, os.O_RDWR | os.O_CREAT | os.O_TRUNC | flags, 0o644)
+        except OSError as e:
+            out[name] = {"error": str(e)}
+            return
+        try:
+            os.ftruncate(fd, total)
+            m = mmap.mmap(fd, total) if use_map else None
+            mnp = np.frombuffer(m, dtype=np.uint8) if use_map else None
+            srcnp = np.frombuffer(mv, dtype=np.uint8)
+            span = total // nt // 4096 * 4096
+            err = []
+
+            def work(t):
+                try:
+                    a, e = t * span, (t + 1) * span
+                    if use_map:
+                        np.copyto(mnp[a:e], srcnp[a:e])
+                        return
+                    o = a
+                    while o < e:
+                        o += os.pwrite(fd, mv[o:min(e, o + (64 << 20))], o)
+                except OSError as ex:
+                    err.append(str(ex))
+
+            t0 = time.perf_counter()
+            th = [threading.Thread(target=work, args=(t,)) for t in range(nt)]
+            for x in th:
+                x.start()
+            for x in th:
+                x.join()
+            dt = time.perf_counter() - t0
+            out[name] = {"error": err[0]} if err else span * nt / dt / 1e9
+            if use_map:
+                del mnp
+                m.close()
+        finally:
+            os.close(fd)
+            try:
+                os.unlink(path)
+            except OSError:
+                pass
+
+    run("buffered_pwrite_1", 0, 1)
+    run("buffered_pwrite_%d" % n_threads, 0, n_threads)
+    run("o_direct_pwrite_%d" % n_threads, os.O_DIRECT, n_threads)
+    run("mmap_copy_%d" % n_threads, 0, n_threads, use_map=True)
+    del per
+    return out
+
+
+# --------------------------------------------------------- config 5, strong scaling ---
+C5 = dict(n=500_000, m=200_000, width=40, seed=5, block=2048)
+C5_N1_FILE = os.path.join(tempfile.gettempdir(), "pgb_config5_n1.json")
+
+
+def run_config5(args, torch, pgb200, lib, dev, rank, world, barrier, cpu_barrier, max_over_ranks):
+    """BASELINE.json configs[4]: 500 000 samples x 200 000 variants (25 GB of records, 400 GB of VCF).
+    Strong scaling: rank r owns variants [r*M/N, (r+1)*M/N); its records are generated on the device and stay
+    resident; K1 + K2 run block by block (2 048 variants = 4.1 GB of text) into a two-buffer output ring.
+    Then ONE call of the product's multi-device path from rank 0 on a slice crossing the 4 GiB record offset."""
+    n, m_all, width, seed, blk = C5["n"], args.config5_variants or C5["m"], C5["width"], C5["seed"], C5["block"]
+    R = synth.record_size(n)
+    L = width + 4 * n + 1
+    lo, hi = rank * m_all // world, (rank + 1) * m_all // world
+    rows = hi - lo
+    stream = torch.cuda.current_stream().cuda_stream
+    recs = torch.empty(rows * R + 64, dtype=torch.uint8, device=dev)
+    recs[rows * R:].zero_()
+    step = 16384
+    for a in range(0, rows, step):
+        pgb200._check(lib.pgb_dev_synth_records_fast(recs.data_ptr() + a * R, R, seed, lo + a, min(step, rows - a), n, stream), "synth")
+    blob_np, off_np = synth.uniform_prefix_blob(rows, lo, width)
+    d_blob = torch.from_numpy(blob_np).to(dev)
+    d_off = torch.from_numpy(off_np.view(np.int64)).to(dev)
+    ring = [torch.empty(blk * L + 1024, dtype=torch.uint8, device=dev) for _ in range(2)]
+    d_meta = torch.zeros((blk + 1) * 4, dtype=torch.int64, device=dev)
+    d_scr = torch.zeros(lib.pgb_dev_index_scratch_bytes(blk) // 8 + 1, dtype=torch.int64, device=dev)
+    variant = int(os.environ.get("PGB_K2_VARIANT", "0"), 0)
+
+    def block(a, out):
+        nb = min(blk, rows - a)
+        pgb200._check(lib.pgb_dev_index_lines(None, d_off.data_ptr() + 8 * a, 0, nb, n, R, d_meta.data_ptr(),
+                                              d_scr.data_ptr(), stream), "K1")
+        pgb200._check(lib.pgb_dev_format_lines_ex(recs.data_ptr() + a * R, R, d_meta.data_ptr(), nb, d_blob.data_ptr(), 0, 0,
+                                                  None, n, width, out.data_ptr(), variant, stream), "K2")
+        return nb
+
+    for i in range(2):  # warm-up
+        if rows:
+            block(0, ring[i])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    launches = 0
+    for i, a in enumerate(range(0, rows, blk)):
+        block(a, ring[i & 1])
+        launches += 4
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    # round trip of the last block on the device: text -> codes -> packed bytes == the records
+    a = (rows - 1) // blk * blk
+    nb = block(a, ring[0])
+    torch.cuda.synchronize()
+    lines = ring[0][:nb * L].view(nb, L)[:min(nb, 64)]
+    gt = lines[:, width:width + 4 * n].reshape(-1, n, 4)
+    lut = torch.full((256, 256), 255, dtype=torch.uint8, device=dev)
+    for code, txt in enumerate([b"00", b"01", b"11", b".."]):
+        lut[txt[0], txt[1]] = code
+    codes = lut[gt[:, :, 1].long(), gt[:, :, 3].long()]
+    shifts = torch.tensor([0, 2, 4, 6], dtype=torch.uint8, device=dev)
+    packed = (codes.view(-1, n // 4, 4) << shifts).sum(dim=2, dtype=torch.uint8)
+    rt_ok = bool(torch.equal(packed, recs[a * R:(a + lines.shape[0]) * R].view(-1, R))) and \
+        bool((gt[:, :, 0] == 9).all()) and bool((lines[:, L - 1] == 10).all()) and \
+        bool(torch.equal(lines[:, :width], d_blob[a * width:(a + lines.shape[0]) * width].view(-1, width)))
+    del lines, gt, codes, packed, lut
+    genotypes = m_all * n
+    value = genotypes / (ms * 1e-3)
+    alg = m_all * (R + width + L)
+    peak, _ = peaks()
+    rec = {"workload": "configs[4]: 500000 samples x %d variants, keep all" % m_all, "scaling": "strong",
+           "variants_per_gpu": rows, "value": value, "unit": UNIT, "ms": ms, "vcf_gb_per_s": m_all * L / (ms * 1e-3) / 1e9,
+           "hbm_gbs_per_gpu": alg / world / (ms * 1e-3) / 1e9, "frac_of_measured_hbm_peak": alg / world / (ms * 1e-3) / 1e9 / peak,
+           "gpu_launches": launches, "block_variants": blk, "output": "two-buffer ring of %.1f GB blocks (400 GB never resident)" % (blk * L / 1e9),
+           "records": "generated on the device (pgb_dev_synth_records_fast), resident in HBM: %.1f GB per GPU" % (rows * R / 1e9),
+           "round_trip_ok": rt_ok, "efficiency_vs_n1": None}
+    if rank == 0:
+        try:
+            if world == 1 and not args.config5_variants:
+                with open(C5_N1_FILE, "w") as f:
+                    json.dump({"value": value, "when": time.time()}, f)
+            elif os.path.exists(C5_N1_FILE) and not args.config5_variants:
+                with open(C5_N1_FILE) as f:
+                    n1 = json.load(f)
+                if time.time() - n1["when"] < 6 * 3600:
+                    rec["efficiency_vs_n1"] = value / n1["value"] / world
+                    rec["n1_value"] = n1["value"]
+        except Exception:
+            pass
+    del ring, recs
+    torch.cuda.empty_cache()
+    torch.cuda.synchronize()
+
+    # ---- the product's own sharding: ONE call from rank 0 over all N devices ----
+    cpu_barrier()  # the other ranks wait on the CPU: nothing of theirs may sit on the GPUs rank 0 is about to use
+    if rank == 0:
+        rec["sharded_call"] = sharded_call(args, torch, pgb200, lib, dev, world, n, R, L, width, seed)
+    cpu_barrier()
+    return rec
+
+
+def sharded_call(args, torch, pgb200, lib, dev, world, n, R, L, width, seed):
+    with open("/proc/meminfo") as f:
+        avail = int(dict(x.split(":") for x in f)["MemAvailable"].split()[0]) * 1024
+    v_slice = args.config5_slice or 16384
+    while v_slice > 512 and v_slice * L + (32768 + v_slice) * R > 0.6 * avail:
+        v_slice //= 2
+    # variants [v0, v0 + v_slice) straddle v = 34 360, where the reference's u32 record offset wraps (pfile.rs:165)
+    v0 = max(0, 34360 - v_slice // 2) if not args.config5_variants else 0
+    m_img = v0 + v_slice
+    stream = torch.cuda.current_stream().cuda_stream
+    t_setup = time.perf_counter()
+    image = torch.empty(12 + m_img * R, dtype=torch.uint8, pin_memory=True)
+    image[:12] = torch.from_numpy(np.frombuffer(synth.pgen_header(m_img, n), dtype=np.uint8).copy())
+    d_img = torch.empty(v_slice * R + 64, dtype=torch.uint8, device=dev)
+    step = min(8192, v_slice)
+    for a in range(0, m_img, step):  # rows outside the slice are generated too: the image is a complete .pgen
+        nb = min(step, m_img - a)
+        pgb200._check(lib.pgb_dev_synth_records_fast(d_img.data_ptr(), R, seed, a, nb, n, stream), "synth")
+        image[12 + a * R:12 + (a + nb) * R].copy_(d_img[:nb * R])
+    pgb200._check(lib.pgb_dev_synth_records_fast(d_img.data_ptr(), R, seed, v0, v_slice, n, stream), "synth")
+    d_img[v_slice * R:].zero_()
+    total = v_slice * L
+    h_out = torch.empty(total + 64, dtype=torch.uint8, pin_memory=True)
+    var = np.arange(v0, v0 + v_slice, dtype=np.uint32)
+    blob_np, off_np = synth.uniform_prefix_blob(v_slice, v0, width)
+    setup_s = time.perf_counter() - t_setup
+    devices = list(range(world))
+    with pgb200.PgenFile(image_ptr=image.data_ptr(), image_bytes=image.numel()) as f:
+        nb, st = f.export_gt_vcf_mem(var, None, blob_np, off_np, h_out.data_ptr(), total, devices=devices)  # warm-up: buffers
+        t0 = time.perf_counter()
+        nb, st = f.export_gt_vcf_mem(var, None, blob_np, off_np, h_out.data_ptr(), total, devices=devices)
+        dt = time.perf_counter() - t0
+    assert nb == total
+    # bit-exact against the device-resident path on device 0, block by block
+    torch.cuda.set_device(dev)
+    d_blob = torch.from_numpy(blob_np).to(dev)
+    d_off = torch.from_numpy(off_np.view(np.int64)).to(dev)
+    blk = 1024
+    d_ref = torch.empty(blk * L + 1024, dtype=torch.uint8, device=dev)
+    d_cmp = torch.empty(blk * L, dtype=torch.uint8, device=dev)
+    d_meta = torch.zeros((blk + 1) * 4, dtype=torch.int64, device=dev)
+    d_scr = torch.zeros(lib.pgb_dev_index_scratch_bytes(blk) // 8 + 1, dtype=torch.int64, device=dev)
+    ok = True
+    for a in range(0, v_slice, blk):
+        nbk = min(blk, v_slice - a)
+        pgb200._check(lib.pgb_dev_index_lines(None, d_off.data_ptr() + 8 * a, 0, nbk, n, R, d_meta.data_ptr(),
+                                              d_scr.data_ptr(), stream), "K1")
+        pgb200._check(lib.pgb_dev_format_lines_ex(d_img.data_ptr() + a * R, R, d_meta.data_ptr(), nbk, d_blob.data_ptr(), 0, 0,
+                                                  None, n, width, d_ref.data_ptr(), 0, stream), "K2")
+        d_cmp[:nbk * L].copy_(h_out[a * L:(a + nbk) * L], non_blocking=True)
+        ok = ok and bool(torch.equal(d_cmp[:nbk * L], d_ref[:nbk * L]))
+    lib.pgb_release_buffers()
+    return {"n_devices": world, "bit_exact": ok, "ms": dt * 1e3, "vcf_gb_per_s": total / dt / 1e9,
+            "genotypes_per_s": v_slice * n / dt, "slice_variants": [int(v0), int(v0 + v_slice)], "slice_bytes": int(total),
+            "record_offsets_cross_4GiB": bool((v0 + v_slice) * R > 2 ** 32 > v0 * R), "chunks": int(st.n_chunks),
+            "api": "pgb_export_gt_vcf_mem(devices=[0..%d]) from one process: page-locked .pgen image in, page-locked body out" % (world - 1),
+            "checked_against": "K1+K2 device-resident on device 0, every byte", "setup_s": setup_s}
+
+
 # ------------------------------------------------------------------------ GPU arm ---
 def run_b200(args, wl, rank, world, local_rank):
     import torch
@@ -266,6 +542,7 @@ def run_b200(args, wl, rank, world, local_rank):
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
+        cpu_pg = dist.new_group(backend="gloo")  # CPU-side barriers: no kernel sits on a GPU while a rank waits
     lib = pgb200.lib
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -321,11 +598,30 @@ def run_b200(args, wl, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def cpu_barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier(group=cpu_pg)
+
     def max_over_ranks(x):
         if dist is None:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def min_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
@@ -367,12 +663,14 @@ def run_b200(args, wl, rank, world, local_rank):
     fb.record()
     torch.cuda.synchronize()
     fill_gbs = 5 * fill_bytes / (fa.elapsed_time(fb) * 1e-3) / 1e9
-    traffic = None
+    traffic = traffic_src = None
     tp = os.path.join(ROOT, "profiles", "k2_traffic.json")
     if os.path.exists(tp):
         try:
             with open(tp) as f:
-                traffic = json.load(f).get(args.workload)
+                tj = json.load(f)
+            traffic = tj.get(args.workload)
+            traffic_src = tj.get("source", "ncu, static (profiles/k2_traffic.json)") if traffic is not None else None
         except Exception:
             traffic = None
 
@@ -392,25 +690,13 @@ def run_b200(args, wl, rank, world, local_rank):
     image[12:].copy_(recs[:m * R])
     torch.cuda.synchronize()
     h_out = torch.empty(total + 64, dtype=torch.uint8, pin_memory=True)
-    # PCIe calibration: ONE plain device->host copy of the whole body into the same page-locked buffer
-    # the export writes (copying a small region repeatedly measures a warmer host path: +10-15 %)
-    # (all ranks at the same time: on a multi-GPU box the host side is shared)
-    cal = total
-    ca, cb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    h_out[:1 << 20].copy_(d_out[:1 << 20], non_blocking=True)
+    # host-side ceilings, measured in this run on all ranks at once (the host side is shared)
+    cal = d2h_calibration(torch, d_out, h_out, total, barrier)
+    d2h_gbs = cal["peak"]
+    n_thr = max(1, min(16, (os.cpu_count() or 2) // max(1, world)))
     barrier()
-    ca.record()
-    h_out[:cal].copy_(d_out[:cal], non_blocking=True)
-    cb.record()
-    torch.cuda.synchronize()
-    d2h_gbs = cal / (ca.elapsed_time(cb) * 1e-3) / 1e9
-    cal1 = min(total, 1 << 30)
-    ca.record()
-    for _ in range(3):
-        h_out[:cal1].copy_(d_out[:cal1], non_blocking=True)
-    cb.record()
-    torch.cuda.synchronize()
-    d2h_small_gbs = 3 * cal1 / (ca.elapsed_time(cb) * 1e-3) / 1e9
+    host_fill_gbs = host_write_probe(h_out.numpy(), n_thr)
+    barrier()
     e2e = None
     with pgb200.PgenFile(image_ptr=image.data_ptr(), image_bytes=image.numel()) as f:
         def e2e_step():
@@ -434,8 +720,12 @@ def run_b200(args, wl, rank, world, local_rank):
                "launches_per_step": int(e_launch // args.steps), "chunks_per_step": int(st.n_chunks),
                "roofline": {"bound": "pcie_d2h", "achieved": total * args.steps / e2e_s / 1e9, "peak": d2h_gbs,
                             "unit": "GB/s per GPU", "frac": total * args.steps / e2e_s / 1e9 / d2h_gbs,
-                            "peak_source": "one cudaMemcpyAsync of the whole body device->pinned host, all ranks concurrently, "
-                                           "measured in this run", "peak_1gib_repeated": d2h_small_gbs}}
+                            "peak_source": "max of {one cudaMemcpyAsync of the whole body, the export's own pattern without kernels "
+                                           "(128 MiB chunks over 3 streams)} device->pinned host, all ranks concurrently, measured in this run",
+                            "whole_body_gbs": cal["whole_body_gbs"], "chunked_3_streams_128MiB_gbs": cal["chunked_3_streams_128MiB_gbs"],
+                            "aggregate_peak_gbs_all_gpus": sum_over_ranks(d2h_gbs),
+                            "host_memory_fill_gbs": host_fill_gbs, "host_memory_fill_threads": n_thr,
+                            "host_memory_fill_note": "CPU threads of this rank filling the same page-locked buffer, all ranks at once"}}
         # parity spot check of the e2e result against the device-resident one (first/last 1 MiB)
         torch.cuda.synchronize()
         k1(); k2()
@@ -444,54 +734,66 @@ def run_b200(args, wl, rank, world, local_rank):
             assert torch.equal(h_out[sl], d_out[sl].cpu()), "e2e and device-resident outputs differ"
         # ---- end to end INCLUDING the file write (north_star's second e2e form): the same call
         #      with an fd sink, as Pfile::output_vcf uses it.  Rank 0, N=1, 1 warm-up + 2 timed.
-        e2e_file = None
-        if rank == 0 and world == 1 and not args.no_file:
-            for where in (os.environ.get("PGB_BENCH_FILE_DIR"), "/dev/shm", tempfile.gettempdir()):
-                if not where or not os.path.isdir(where):
-                    continue
+        # ---- end to end INCLUDING the file write (north_star's second e2e form): the same call with an fd sink,
+        #      as Pfile::output_vcf uses it; every rank writes its own file at the same time.  1 warm-up + 2 timed.
+        def file_leg(where, kind):
+            ok = os.path.isdir(where)
+            if ok:
                 vfs = os.statvfs(where)
-                if vfs.f_bavail * vfs.f_frsize < total + (2 << 30):
-                    continue
-                path = os.path.join(where, "pgb_bench_%d.vcf" % os.getpid())
-                try:
-                    # storage calibration: plain pwrite() of the finished body from page-locked memory
-                    # into a fresh file on the same file system, one thread, no fsync
-                    mv = memoryview(h_out.numpy())[:min(total, 4 << 30)]
+                ok = vfs.f_bavail * vfs.f_frsize >= world * total + (4 << 30)
+            if min_over_ranks(1.0 if ok else 0.0) < 1.0:
+                return None
+            path = os.path.join(where, "pgb_bench_%d_%d.vcf" % (os.getpid(), rank))
+            try:
+                # raw sink rates for the same bytes, all ranks at once, on the same file system
+                mv = memoryview(h_out.numpy())[:min(total, (4 << 30) // world)]
+                barrier()
+                ceil = file_sink_ceilings(path + ".probe", mv, n_thr)
+                best = max([v for v in ceil.values() if isinstance(v, float)] or [0.0])
+                agg_best = sum_over_ranks(best)
+                ts = []
+                for it in range(3):
                     fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
                     try:
+                        barrier()
                         t0 = time.perf_counter()
-                        o = 0
-                        while o < len(mv):
-                            o += os.pwrite(fd, mv[o:o + (256 << 20)], o)
-                        pw_gbs = len(mv) / (time.perf_counter() - t0) / 1e9
+                        stf = f.export_gt_vcf(var, sam, blob_np, off_np, fd, devices=[local_rank])
+                        ts.append(max_over_ranks(time.perf_counter() - t0))
                     finally:
                         os.close(fd)
-                    ts = []
-                    for it in range(3):
-                        fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
-                        try:
-                            t0 = time.perf_counter()
-                            stf = f.export_gt_vcf(var, sam, blob_np, off_np, fd, devices=[local_rank])
-                            ts.append(time.perf_counter() - t0)
-                        finally:
-                            os.close(fd)
-                        assert os.path.getsize(path) == total
-                    with open(path, "rb") as fh:  # spot check against the in-memory result
-                        assert fh.read(1 << 20) == bytes(h_out[:1 << 20].numpy())
-                    tt = sum(ts[1:]) / 2
-                    e2e_file = {"value": genotypes_step / tt, "unit": UNIT, "vcf_gb_per_s": total / tt / 1e9,
-                                "ms_per_step": 1e3 * tt, "sink": "regular file in %s (%s), no fsync" % (
-                                    where, "tmpfs" if where == "/dev/shm" else "page cache"),
-                                "api": "pgb_export_gt_vcf (fd sink; tmpfs: parallel copies through a mapping, else pwrite)", "chunks": int(stf.n_chunks),
-                                "roofline": {"bound": "storage", "achieved": total / tt / 1e9, "peak": pw_gbs, "unit": "GB/s",
-                                             "frac": total / tt / 1e9 / pw_gbs,
-                                             "peak_source": "reference point, not a ceiling: ONE thread pwrite()ing the same bytes to the same "
-                                                            "file system, measured in this run (parallel writers can exceed it)"}}
-                finally:
-                    if os.path.exists(path):
-                        os.unlink(path)
-                break
+                    assert os.path.getsize(path) == total
+                with open(path, "rb") as fh:  # spot check against the in-memory result
+                    assert fh.read(1 << 20) == bytes(h_out[:1 << 20].numpy())
+                tt = sum(ts[1:]) / 2
+                return {"value": world * genotypes_step / tt, "unit": UNIT, "vcf_gb_per_s": world * total / tt / 1e9,
+                        "ms_per_step": 1e3 * tt, "sink": "one regular file per rank in %s (%s), no fsync" % (where, kind),
+                        "api": "pgb_export_gt_vcf (fd sink)", "chunks": int(stf.n_chunks),
+                        "roofline": {"bound": "storage", "achieved": world * total / tt / 1e9, "peak": agg_best, "unit": "GB/s (all ranks)",
+                                     "frac": world * total / tt / 1e9 / agg_best if agg_best else None,
+                                     "peak_source": "best raw sink rate of the same bytes without the GPU, all ranks at once, measured in this "
+                                                    "run: max over {1 buffered pwrite thread, N buffered pwrite threads, N O_DIRECT pwrite "
+                                                    "threads, N copies through a MAP_SHARED mapping}, N = %d per rank" % n_thr,
+                                     "rank0_sink_rates_gbs": ceil}}
+            finally:
+                for q in (path, path + ".probe"):
+                    if os.path.exists(q):
+                        os.unlink(q)
+
+        e2e_file = e2e_file_disk = None
+        if not args.no_file:
+            shm = os.environ.get("PGB_BENCH_FILE_DIR") or "/dev/shm"
+            e2e_file = file_leg(shm, "tmpfs" if shm == "/dev/shm" else "PGB_BENCH_FILE_DIR")
+            disk = tempfile.gettempdir()
+            if os.path.isdir(disk) and os.stat(disk).st_dev != os.stat(shm).st_dev:
+                e2e_file_disk = file_leg(disk, "block-device file system, page cache")
     clocks = sampler.stop() if sampler else None
+
+    # ---- configs[4] (biobank shape), strong scaling + the product's own multi-device call ----
+    config5 = None
+    if not args.no_config5:
+        del d_out, recs, h_out, image, d_blob, d_off, d_meta, d_scr
+        torch.cuda.empty_cache()
+        config5 = run_config5(args, torch, pgb200, lib, dev, rank, world, barrier, cpu_barrier, max_over_ranks)
 
     # ---- CPU baseline beside it (rank 0, N=1 only) ----
     cpu = None
@@ -514,10 +816,12 @@ def run_b200(args, wl, rank, world, local_rank):
                        "l2": "inputs (0.69 GB records) and output (>= 0.5 GB) exceed the 126 MB L2; no flush needed"},
             "vcf_gb_per_s": world * total * args.steps / (dev_ms * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k2_format_kernel", "kernel_ms": k2_ms,
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": "k2_batch_kernel" if (sam is not None or width + 4 * K + 1 <= 3072) else "k2_format_kernel",
+                         "kernel_ms": k2_ms,
                          "algorithmic_bytes_per_launch": int(alg_bytes), "peak_source": peak_src,
                          "frac_of_nominal_8TBs": achieved / 8000.0, "store_only_ceiling_gbs": fill_gbs},
-            "e2e": e2e, "e2e_file": e2e_file, "cpu_baseline": cpu, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+            "e2e": e2e, "e2e_file": e2e_file, "e2e_file_disk": e2e_file_disk, "config5": config5, "cpu_baseline": cpu, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -536,6 +840,9 @@ def main():
     ap.add_argument("--n-samples", type=int, default=0, help="kernel development: override the workload's sample count")
     ap.add_argument("--n-variants", type=int, default=0, help="kernel development: override the workload's variant count")
     ap.add_argument("--no-e2e", action="store_true", help="kernel development: device-resident part only, short line")
+    ap.add_argument("--no-config5", action="store_true", help="skip the configs[4] strong-scaling leg")
+    ap.add_argument("--config5-variants", type=int, default=0, help="development: shrink configs[4] to this many variants")
+    ap.add_argument("--config5-slice", type=int, default=0, help="variants of the slice given to the multi-device call (default 16384)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -238,6 +238,11 @@ int pgb_dev_format_lines_ex(const uint8_t *records, uint32_t record_bytes, const
 int pgb_dev_synth_records(uint8_t *records, uint64_t pitch, uint64_t seed, uint64_t row0, uint64_t n_rows,
                           uint32_t n_samples, void *stream);
 
+/* A cheaper synthetic generator for the biobank shape (tools/synth.py: synth_records_fast): one 32-bit hash per
+ * four record bytes, uniform over the four genotype codes, padding samples 0. */
+int pgb_dev_synth_records_fast(uint8_t *records, uint64_t pitch, uint32_t seed, uint64_t row0, uint64_t n_rows,
+                               uint32_t n_samples, void *stream);
+
 /* Store-only calibration kernel (16-byte streaming stores of a constant). */
 int pgb_dev_fill(uint8_t *dst, uint64_t bytes, int variant, void *stream);
 

@@ -494,6 +494,44 @@ __global__ void __launch_bounds__(256) synth_records_kernel(uint8_t *__restrict_
     }
 }
 
+// Cheap generator for the biobank shape (25 GB of records have to be produced on the device before the timed
+// region): one murmur3 finaliser per 32-bit word (16 samples), documented in tools/synth.py (synth_records_fast is
+// its numpy twin).  Every byte pattern occurs; the genotype distribution is uniform over the four codes.
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16;
+    h *= 0x85EBCA6Bu;
+    h ^= h >> 13;
+    h *= 0xC2B2AE35u;
+    return h ^ (h >> 16);
+}
+
+__global__ void __launch_bounds__(256) synth_fast_kernel(uint8_t *__restrict__ records, uint64_t pitch, uint32_t seed,
+                                                         uint64_t row0, uint64_t n_rows, uint32_t n_samples, uint32_t R) {
+    const uint32_t words = (R + 3u) / 4u;
+    const uint64_t total = n_rows * (uint64_t)words;
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t row = idx / words;
+        const uint32_t w = (uint32_t)(idx - row * words);
+        const uint32_t v = (uint32_t)(row0 + row);
+        const uint32_t h = fmix32(seed * 0x9E3779B1u ^ v * 0x85EBCA77u ^ (w + 1u) * 0xC2B2AE3Du);
+        uint8_t *dst = records + row * pitch + 4ull * w;
+        if ((((uintptr_t)dst) & 3u) == 0 && 4u * w + 4u <= R && 16u * w + 16u <= n_samples) { // a whole aligned word
+            *reinterpret_cast<uint32_t *>(dst) = h;
+            continue;
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t j = 4u * w + k;
+            if (j >= R) break;
+            uint32_t byte = (h >> (8u * k)) & 0xFFu;
+            const uint32_t first = 4u * j; // samples first .. first + 3; padding samples (>= n_samples) are 0
+            if (first + 4u > n_samples) byte &= (1u << (2u * (n_samples - first))) - 1u;
+            dst[k] = (uint8_t)byte;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) fill_kernel(uint8_t *dst, uint64_t n16, int hint) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride)
@@ -783,6 +821,18 @@ extern "C" int pgb_dev_synth_records(uint8_t *records, uint64_t pitch, uint64_t 
     synth_records_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(records, pitch, seed, row0, n_rows, n_samples,
                                                                             R);
     return check_launch("synth_records_kernel");
+}
+
+extern "C" int pgb_dev_synth_records_fast(uint8_t *records, uint64_t pitch, uint32_t seed, uint64_t row0, uint64_t n_rows,
+                                          uint32_t n_samples, void *stream) {
+    const uint32_t R = pgb_record_bytes(n_samples);
+    if (!records || pitch < R) return PGB_E_ARG;
+    const uint64_t total = n_rows * (uint64_t)((R + 3u) / 4u);
+    if (total == 0) return PGB_OK;
+    uint64_t blocks = (total + 255) / 256;
+    if (blocks > 148ull * 64) blocks = 148ull * 64;
+    synth_fast_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(records, pitch, seed, row0, n_rows, n_samples, R);
+    return check_launch("synth_fast_kernel");
 }
 
 // variant: bits 0-3 store hint (0 default, 1 .cs streaming).

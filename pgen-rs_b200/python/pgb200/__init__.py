@@ -101,6 +101,7 @@ SYMBOLS = {
     "pgb_dev_index_lines_ex": (_i, [_vp, _vp, _u64, _vp, _vp, _u32, _u64, _u64, _u32, _vp, _vp, _vp]),
     "pgb_dev_format_lines_ex": (_i, [_vp, _u32, _vp, _u64, _vp, _u32, _u32, _vp, _u32, _u32, _vp, _i, _vp]),
     "pgb_dev_synth_records": (_i, [_vp, _u64, _u64, _u64, _u64, _u32, _vp]),
+    "pgb_dev_synth_records_fast": (_i, [_vp, _u64, _u32, _u64, _u64, _u32, _vp]),
     "pgb_dev_fill": (_i, [_vp, _u64, _i, _vp]),
     "pgb_dev_fill_pattern": (_i, [_vp, _u64, _u32, _u32, _u32, _u32, _i, _vp]),
     "pgb_device_count": (_i, []),

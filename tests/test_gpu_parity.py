@@ -227,8 +227,9 @@ def test_k0_k1_synth_device_level(pgb, torch_cuda):
         assert (meta[:-1, 1] == rows.astype(np.uint64) * pitch).all()
         assert (meta[:-1, 2] == off[:-1] - base).all()
         assert ((meta[:-1, 3] & 0xFFFFFFFF) == plen).all()
-    # synthetic generator: device == numpy
-    for n, rows0, nrows, pitch_pad in [(2504, 0, 300, 0), (5, 7, 64, 3), (300, 100000, 257, 5), (70001, 3, 9, 0)]:
+    # synthetic generators: device == numpy
+    for n, rows0, nrows, pitch_pad in [(2504, 0, 300, 0), (5, 7, 64, 3), (300, 100000, 257, 5), (70001, 3, 9, 0),
+                                       (500000, 199990, 10, 0), (6, 0, 33, 2)]:
         r = synth.record_size(n)
         pitch = r + pitch_pad
         d = torch.zeros(nrows * pitch, dtype=torch.uint8, device="cuda")
@@ -236,6 +237,11 @@ def test_k0_k1_synth_device_level(pgb, torch_cuda):
         torch.cuda.synchronize()
         got = d.cpu().numpy().reshape(nrows, pitch)[:, :r]
         assert (got == synth.synth_records(42, rows0, nrows, n)).all()
+        d.zero_()
+        assert pgb.lib.pgb_dev_synth_records_fast(d.data_ptr(), pitch, 42, rows0, nrows, n, 0) == 0
+        torch.cuda.synchronize()
+        full = d.cpu().numpy().reshape(nrows, pitch)
+        assert (full[:, :r] == synth.synth_records_fast(42, rows0, nrows, n)).all() and (full[:, r:] == 0).all()
 
 
 def _device_run(pgb, torch, recs_dev, pitch, n, var_rows, kidx_np, blob, off, max_pfx, variant=0):
