@@ -116,6 +116,19 @@ int pgb_export_gt_vcf_mem(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, 
                           uint64_t n_sam, const uint8_t *prefix_blob, const uint64_t *prefix_off, uint8_t *out_buf,
                           uint64_t out_cap, uint64_t *out_len, const int *device_ids, int n_devices, pgb_stats *stats);
 
+/* The same export with the line prefixes BUILT ON THE DEVICE from the raw .pvar image: kept variant i's prefix is
+ * pvar_text[row_off[i] .. row_off[i] + row_len[i]) — the row as it is in the file, without its line terminator:
+ * for a table without csv quoting that is every field followed by '\t' except the last (src/pfile.rs:157-160) —
+ * followed by "\tGT" (src/pfile.rs:160-161), which K2 appends.  No per-row host pass builds a prefix blob; the
+ * host only hands over the offsets its .pvar reader already has.  row_off need not be ascending. */
+int pgb_export_gt_vcf_rows(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint32_t *sam_idx, uint64_t n_sam,
+                           const uint8_t *pvar_text, uint64_t pvar_bytes, const uint64_t *row_off, const uint32_t *row_len,
+                           int out_fd, const int *device_ids, int n_devices, pgb_stats *stats);
+int pgb_export_gt_vcf_rows_mem(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint32_t *sam_idx,
+                               uint64_t n_sam, const uint8_t *pvar_text, uint64_t pvar_bytes, const uint64_t *row_off,
+                               const uint32_t *row_len, uint8_t *out_buf, uint64_t out_cap, uint64_t *out_len,
+                               const int *device_ids, int n_devices, pgb_stats *stats);
+
 /* The multi-GPU partition pgb_export_gt_vcf uses: the kept-variant list cut into n_shards
  * contiguous ranges balanced by output bytes.  line_begin (n_shards+1 entries) receives the
  * range boundaries, byte_begin (optional, n_shards+1) the body offset at which each range
@@ -152,6 +165,12 @@ uint64_t pgb_plan_n_sam(const pgb_plan *p);
 const uint32_t *pgb_plan_var_idx(const pgb_plan *p);
 const uint32_t *pgb_plan_sam_idx(const pgb_plan *p);
 const uint8_t *pgb_plan_header(const pgb_plan *p, uint64_t *len);
+/* the raw .pvar image and the kept rows in it: what output_vcf hands to pgb_export_gt_vcf_rows */
+const uint8_t *pgb_plan_pvar_text(const pgb_plan *p, uint64_t *len);
+const uint64_t *pgb_plan_row_off(const pgb_plan *p);
+const uint32_t *pgb_plan_row_len(const pgb_plan *p);
+/* the finished prefixes (row + "\tGT") as a blob with n_var + 1 offsets: built on first use, for callers of
+ * pgb_export_gt_vcf and for tests; output_vcf itself no longer builds it */
 const uint8_t *pgb_plan_prefix_blob(const pgb_plan *p, uint64_t *len);
 const uint64_t *pgb_plan_prefix_off(const pgb_plan *p);
 

@@ -205,6 +205,10 @@ struct Chunk {
     bool dense;          // true: stage the covering byte range; false: stage kept rows compactly
     uint64_t in_bytes;   // record bytes staged
     uint32_t max_pfx;
+    // rows mode (prefixes built on the device from raw .pvar rows): the staged text
+    uint64_t t0 = 0;         // offset in the .pvar image of the first staged byte (text_dense)
+    uint64_t text_bytes = 0; // covering range (text_dense) or the kept rows packed back to back
+    bool text_dense = false;
 };
 
 class WritePool;
@@ -230,7 +234,12 @@ struct Job {
     const uint32_t *sam_idx; // nullptr => all
     uint64_t K;
     const uint8_t *prefix_blob;
-    const uint64_t *prefix_off;
+    const uint64_t *prefix_off; // blob mode: the caller's offsets; rows mode: cumulative prefix lengths (row_len + suffix)
+    // rows mode: line i's prefix is text[row_off[i] .. + row_len[i]) followed by the suffix ("\tGT"), appended by K2
+    const uint8_t *text = nullptr;
+    const uint64_t *row_off = nullptr;
+    const uint32_t *row_len = nullptr;
+    uint32_t sfx = 0, sfx_len = 0;
     Sink *sink;
     int variant;
     bool trace = false;
@@ -407,9 +416,10 @@ class WritePool {
     bool stop_ = false;
 };
 
-// Stage layout inside h_in/d_in:  [records | pad16 | prefix bytes | prefix_off u64[n+1] | var_row u32[n]]
+// Stage layout inside h_in/d_in:  [records | pad16 | prefix bytes (or .pvar text) | pad16 | prefix_off u64[n+1] |
+//                                   prefix_len u32[n] (rows mode, dense text) | var_row u32[n]]
 struct Stage {
-    uint64_t rec_bytes, pfx_pos, pfx_bytes, off_pos, row_pos, total;
+    uint64_t rec_bytes, pfx_pos, pfx_bytes, off_pos, len_pos, row_pos, total;
 };
 
 Stage stage_layout(const Job &j, const Chunk &c, bool records_inline) {
@@ -417,9 +427,10 @@ Stage stage_layout(const Job &j, const Chunk &c, bool records_inline) {
     s.rec_bytes = records_inline ? c.in_bytes : 0;
     uint64_t n = c.b - c.a;
     s.pfx_pos = align_up(s.rec_bytes + 16, kAlign);
-    s.pfx_bytes = j.prefix_off[c.b] - j.prefix_off[c.a];
-    s.off_pos = align_up(s.pfx_pos + s.pfx_bytes, kAlign);
-    s.row_pos = align_up(s.off_pos + (n + 1) * 8, kAlign);
+    s.pfx_bytes = j.text ? c.text_bytes : j.prefix_off[c.b] - j.prefix_off[c.a];
+    s.off_pos = align_up(s.pfx_pos + s.pfx_bytes + 16, kAlign);
+    s.len_pos = align_up(s.off_pos + (n + 1) * 8, kAlign);
+    s.row_pos = align_up(s.len_pos + (j.text && c.text_dense ? n * 4 : 0), kAlign);
     // per-line record index input of K1: u32 row numbers (fixed-width) or u64 byte offsets (standard format)
     s.total = align_up(s.row_pos + (c.dense ? n * (j.f->standard ? 8 : 4) : 0), kAlign);
     return s;
@@ -577,8 +588,31 @@ int run_device_inner(Job *job, DeviceWork *w, std::deque<Pending> &q, std::mutex
             }
             memset(h + lay.rec_bytes, 0, 16);
         }
-        memcpy(h + lay.pfx_pos, job->prefix_blob + job->prefix_off[ch.a], lay.pfx_bytes);
-        memcpy(h + lay.off_pos, job->prefix_off + ch.a, (n + 1) * 8);
+        if (!job->text) {
+            memcpy(h + lay.pfx_pos, job->prefix_blob + job->prefix_off[ch.a], lay.pfx_bytes);
+            memcpy(h + lay.off_pos, job->prefix_off + ch.a, (n + 1) * 8);
+        } else if (ch.text_dense) {
+            // the covering range of the .pvar image as it is in the file; K1 gets (offset, length) per line
+            memcpy(h + lay.pfx_pos, job->text + ch.t0, lay.pfx_bytes);
+            uint64_t *po = (uint64_t *)(h + lay.off_pos);
+            uint32_t *pl = (uint32_t *)(h + lay.len_pos);
+            for (uint64_t i = 0; i < n; i++) {
+                po[i] = job->row_off[ch.a + i] - ch.t0;
+                pl[i] = job->row_len[ch.a + i];
+            }
+            po[n] = 0;
+        } else {
+            // sparse selection: the kept rows packed back to back (still without the suffix)
+            uint64_t *po = (uint64_t *)(h + lay.off_pos);
+            uint64_t at = 0;
+            for (uint64_t i = 0; i < n; i++) {
+                po[i] = at;
+                memcpy(h + lay.pfx_pos + at, job->text + job->row_off[ch.a + i], job->row_len[ch.a + i]);
+                at += job->row_len[ch.a + i];
+            }
+            po[n] = at;
+        }
+        memset(h + lay.pfx_pos + lay.pfx_bytes, 0, 16);
         if (ch.dense && f->standard) {
             uint64_t *ro = (uint64_t *)(h + lay.row_pos);
             for (uint64_t i = 0; i < n; i++) ro[i] = f->rec_off(job->var_idx ? job->var_idx[ch.a + i] : ch.a + i) - ch.o0;
@@ -605,16 +639,17 @@ int run_device_inner(Job *job, DeviceWork *w, std::deque<Pending> &q, std::mutex
         CU(cudaMemcpyAsync(d_stage, h, lay.total, cudaMemcpyHostToDevice, st));
         w->h2d += lay.total;
         CU(cudaEventRecord(s.ev_k0, st));
-        if (ch.dense && f->standard)
-            rc = pgb_dev_index_lines_off((const uint64_t *)(d_stage + lay.row_pos), (const uint64_t *)(d_stage + lay.off_pos),
-                                         job->prefix_off[ch.a], n, (uint32_t)K, s.d_meta, s.d_scratch, st);
-        else
-            rc = pgb_dev_index_lines(ch.dense ? (const uint32_t *)(d_stage + lay.row_pos) : nullptr,
-                                     (const uint64_t *)(d_stage + lay.off_pos), job->prefix_off[ch.a], n, (uint32_t)K, R,
-                                     s.d_meta, s.d_scratch, st);
+        {
+            const bool rows_dense = job->text && ch.text_dense;
+            const uint64_t *d_rec_off = ch.dense && f->standard ? (const uint64_t *)(d_stage + lay.row_pos) : nullptr;
+            const uint32_t *d_var_row = ch.dense && !f->standard ? (const uint32_t *)(d_stage + lay.row_pos) : nullptr;
+            rc = pgb_dev_index_lines_ex(d_var_row, d_rec_off, R, (const uint64_t *)(d_stage + lay.off_pos),
+                                        rows_dense ? (const uint32_t *)(d_stage + lay.len_pos) : nullptr, job->sfx_len,
+                                        job->text ? 0 : job->prefix_off[ch.a], n, (uint32_t)K, s.d_meta, s.d_scratch, st);
+        }
         if (rc) return rc;
-        rc = pgb_dev_format_lines_ex(d_records, R, s.d_meta, n, d_stage + lay.pfx_pos, 0, 0, gather ? c->d_kidx : nullptr,
-                                     (uint32_t)K, ch.max_pfx, s.d_out, job->variant, st);
+        rc = pgb_dev_format_lines_ex(d_records, R, s.d_meta, n, d_stage + lay.pfx_pos, job->sfx, job->sfx_len,
+                                     gather ? c->d_kidx : nullptr, (uint32_t)K, ch.max_pfx, s.d_out, job->variant, st);
         if (rc) return rc;
         CU(cudaEventRecord(s.ev_k1, st));
         w->launches += 4;
@@ -666,9 +701,41 @@ void run_device(Job *job, DeviceWork *w) {
     if (job->status.load() != PGB_OK) cudaGetLastError(); // clear a sticky non-fatal error state
 }
 
+// Where the line prefixes (pfile.rs:157-161) come from: a blob of finished prefixes with n_var + 1 offsets, or the
+// raw .pvar image with one (offset, length) per kept row — then the "\tGT" that ends every prefix is appended
+// on the device and no per-row host pass builds a blob.
+struct PrefixSrc {
+    const uint8_t *blob = nullptr;
+    const uint64_t *off = nullptr;
+    const uint8_t *text = nullptr;
+    uint64_t text_bytes = 0;
+    const uint64_t *row_off = nullptr;
+    const uint32_t *row_len = nullptr;
+};
+
 int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint32_t *sam_idx, uint64_t n_sam,
-                const uint8_t *prefix_blob, const uint64_t *prefix_off, Sink *sink, uint64_t out_cap, uint64_t *out_len,
-                const int *device_ids, int n_devices, pgb_stats *stats) {
+                const PrefixSrc &pfx, Sink *sink, uint64_t out_cap, uint64_t *out_len, const int *device_ids, int n_devices,
+                pgb_stats *stats) {
+    const uint8_t *prefix_blob = pfx.blob;
+    const uint64_t *prefix_off = pfx.off;
+    const bool rows_mode = pfx.text != nullptr || pfx.row_off != nullptr;
+    constexpr uint32_t kSfx = 0x00544709u, kSfxLen = 3; // "\tGT"
+    std::vector<uint64_t> cum; // rows mode: cumulative prefix lengths stand in for prefix_off
+    if (rows_mode) {
+        if (n_var && (!pfx.row_off || !pfx.row_len || !pfx.text)) { pgb_set_error("row_off / row_len / pvar_text is NULL"); return PGB_E_ARG; }
+        cum.resize(n_var + 1);
+        uint64_t at = 0;
+        for (uint64_t i = 0; i < n_var; i++) {
+            if (pfx.row_off[i] > pfx.text_bytes || pfx.row_len[i] > pfx.text_bytes - pfx.row_off[i] || pfx.row_len[i] > 0x7ffffff0u) {
+                pgb_set_error("row %llu lies outside the .pvar image", (unsigned long long)i);
+                return PGB_E_RANGE;
+            }
+            cum[i] = at;
+            at += (uint64_t)pfx.row_len[i] + kSfxLen;
+        }
+        cum[n_var] = at;
+        prefix_off = cum.data();
+    }
     const auto t_begin = std::chrono::steady_clock::now();
     const bool trace = env_u64("PGB_TRACE", 0) != 0;
     auto lap = [&](const char *what) {
@@ -717,7 +784,7 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
         }
     }
     if (n_var) total_pfx = prefix_off[n_var] - prefix_off[0];
-    if (total_pfx && !prefix_blob) return PGB_E_ARG;
+    if (total_pfx && !prefix_blob && !rows_mode) return PGB_E_ARG;
     const uint64_t fixed = 4ull * K + 1ull;
     const uint64_t total = total_pfx + n_var * fixed;
     if (out_len) *out_len = total;
@@ -775,6 +842,7 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
             uint64_t b = line + 1;
             uint64_t omin = f->rec_off(var_idx ? var_idx[line] : line), omax = omin;
             uint32_t maxp = (uint32_t)(prefix_off[line + 1] - prefix_off[line]);
+            uint64_t tmin = rows_mode ? pfx.row_off[line] : 0, tmax = rows_mode ? pfx.row_off[line] + pfx.row_len[line] : 0;
             while (b < end) {
                 const uint64_t ob = out_before(b + 1) - out_before(line);
                 if (ob > chunk_out) break;
@@ -785,6 +853,10 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
                 if (!f->standard && (nmax - nmin) / (R ? R : 1) >= 0xffffffffull) break;
                 omin = nmin; omax = nmax;
                 maxp = std::max(maxp, (uint32_t)(prefix_off[b + 1] - prefix_off[b]));
+                if (rows_mode) {
+                    tmin = std::min(tmin, pfx.row_off[b]);
+                    tmax = std::max(tmax, pfx.row_off[b] + pfx.row_len[b]);
+                }
                 b++;
             }
             c.b = b;
@@ -797,6 +869,14 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
             c.out_off = out_before(line);
             c.out_bytes = out_before(b) - c.out_off;
             c.max_pfx = maxp;
+            if (rows_mode) {
+                // rows of a dense selection: DMA the covering range of the .pvar image as it is (the rows between
+                // kept rows and the line terminators travel along); sparse: the kept rows packed on the host
+                const uint64_t kept_text = (prefix_off[b] - prefix_off[line]) - (b - line) * kSfxLen;
+                c.text_dense = tmax - tmin <= 4 * kept_text + 4096;
+                c.t0 = tmin;
+                c.text_bytes = c.text_dense ? tmax - tmin : kept_text;
+            }
             work[g].chunks.push_back(c);
             seq++;
             line = b;
@@ -807,6 +887,10 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
     Job job;
     job.f = f; job.var_idx = var_idx; job.n_var = n_var; job.sam_idx = sam_idx; job.K = K;
     job.prefix_blob = prefix_blob; job.prefix_off = prefix_off; job.sink = sink;
+    if (rows_mode) {
+        job.text = pfx.text; job.row_off = pfx.row_off; job.row_len = pfx.row_len;
+        job.sfx = kSfx; job.sfx_len = kSfxLen;
+    }
     job.variant = (int)env_u64("PGB_K2_VARIANT", 0);
     job.trace = trace;
     job.t0 = t_begin;
@@ -1026,8 +1110,52 @@ extern "C" int pgb_export_gt_vcf(pgb_file *f, const uint32_t *var_idx, uint64_t 
     int fl = fcntl(out_fd, F_GETFL);
     sink.positional = cur >= 0 && fl >= 0 && !(fl & O_APPEND);
     sink.base = cur >= 0 ? (uint64_t)cur : 0;
-    return export_impl(f, var_idx, n_var, sam_idx, n_sam, prefix_blob, prefix_off, &sink, 0, nullptr, device_ids,
-                       n_devices, stats);
+    PrefixSrc pfx;
+    pfx.blob = prefix_blob;
+    pfx.off = prefix_off;
+    return export_impl(f, var_idx, n_var, sam_idx, n_sam, pfx, &sink, 0, nullptr, device_ids, n_devices, stats);
+}
+
+static void fd_sink(Sink *sink, int out_fd) {
+    sink->fd = out_fd;
+    off_t cur = lseek(out_fd, 0, SEEK_CUR);
+    int fl = fcntl(out_fd, F_GETFL);
+    sink->positional = cur >= 0 && fl >= 0 && !(fl & O_APPEND);
+    sink->base = cur >= 0 ? (uint64_t)cur : 0;
+}
+
+extern "C" int pgb_export_gt_vcf_rows(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint32_t *sam_idx,
+                                      uint64_t n_sam, const uint8_t *pvar_text, uint64_t pvar_bytes, const uint64_t *row_off,
+                                      const uint32_t *row_len, int out_fd, const int *device_ids, int n_devices,
+                                      pgb_stats *stats) {
+    if (out_fd < 0) return PGB_E_ARG;
+    Sink sink;
+    fd_sink(&sink, out_fd);
+    static const uint8_t empty = 0;
+    PrefixSrc pfx;
+    pfx.text = pvar_text ? pvar_text : &empty;
+    pfx.text_bytes = pvar_text ? pvar_bytes : 0;
+    pfx.row_off = row_off;
+    pfx.row_len = row_len;
+    return export_impl(f, var_idx, n_var, sam_idx, n_sam, pfx, &sink, 0, nullptr, device_ids, n_devices, stats);
+}
+
+extern "C" int pgb_export_gt_vcf_rows_mem(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint32_t *sam_idx,
+                                          uint64_t n_sam, const uint8_t *pvar_text, uint64_t pvar_bytes,
+                                          const uint64_t *row_off, const uint32_t *row_len, uint8_t *out_buf, uint64_t out_cap,
+                                          uint64_t *out_len, const int *device_ids, int n_devices, pgb_stats *stats) {
+    if (!out_buf && out_cap) return PGB_E_ARG;
+    Sink sink;
+    static uint8_t dummy;
+    static const uint8_t empty = 0;
+    sink.mem = out_buf ? out_buf : &dummy;
+    sink.mem_pinned = out_buf && is_pinned(out_buf);
+    PrefixSrc pfx;
+    pfx.text = pvar_text ? pvar_text : &empty;
+    pfx.text_bytes = pvar_text ? pvar_bytes : 0;
+    pfx.row_off = row_off;
+    pfx.row_len = row_len;
+    return export_impl(f, var_idx, n_var, sam_idx, n_sam, pfx, &sink, out_cap, out_len, device_ids, n_devices, stats);
 }
 
 extern "C" int pgb_export_gt_vcf_mem(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint32_t *sam_idx,
@@ -1039,6 +1167,8 @@ extern "C" int pgb_export_gt_vcf_mem(pgb_file *f, const uint32_t *var_idx, uint6
     static uint8_t dummy;
     sink.mem = out_buf ? out_buf : &dummy;
     sink.mem_pinned = out_buf && is_pinned(out_buf);
-    return export_impl(f, var_idx, n_var, sam_idx, n_sam, prefix_blob, prefix_off, &sink, out_cap, out_len, device_ids,
-                       n_devices, stats);
+    PrefixSrc pfx;
+    pfx.blob = prefix_blob;
+    pfx.off = prefix_off;
+    return export_impl(f, var_idx, n_var, sam_idx, n_sam, pfx, &sink, out_cap, out_len, device_ids, n_devices, stats);
 }

@@ -74,9 +74,21 @@ extern "C" const uint8_t *pgb_plan_header(const pgb_plan *p, uint64_t *len) {
     if (len) *len = p->plan.header.size();
     return (const uint8_t *)p->plan.header.data();
 }
+extern "C" const uint8_t *pgb_plan_pvar_text(const pgb_plan *p, uint64_t *len) {
+    if (!p) return nullptr;
+    if (len) *len = p->plan.pvar_text.size();
+    return (const uint8_t *)p->plan.pvar_text.data();
+}
+extern "C" const uint64_t *pgb_plan_row_off(const pgb_plan *p) { return p ? p->plan.row_off.data() : nullptr; }
+extern "C" const uint32_t *pgb_plan_row_len(const pgb_plan *p) { return p ? p->plan.row_len.data() : nullptr; }
 extern "C" const uint8_t *pgb_plan_prefix_blob(const pgb_plan *p, uint64_t *len) {
     if (!p) return nullptr;
+    const_cast<pgb_plan *>(p)->plan.materialize_prefixes();
     if (len) *len = p->plan.prefix_blob.size();
     return p->plan.prefix_blob.data();
 }
-extern "C" const uint64_t *pgb_plan_prefix_off(const pgb_plan *p) { return p ? p->plan.prefix_off.data() : nullptr; }
+extern "C" const uint64_t *pgb_plan_prefix_off(const pgb_plan *p) {
+    if (!p) return nullptr;
+    const_cast<pgb_plan *>(p)->plan.materialize_prefixes();
+    return p->plan.prefix_off.data();
+}

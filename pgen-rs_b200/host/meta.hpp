@@ -48,6 +48,11 @@ class MetaTable {
     // The record's text without its terminator: the fields joined by '\t', exactly as in the file.
     std::string_view row_text(size_t row) const { return std::string_view(data_.data() + rows_[row].off, rows_[row].len); }
     void row(size_t r, std::vector<std::string_view> *out) const;
+    // Position of a record in data(): what the device needs to build the line prefix from the raw image.
+    uint64_t row_offset(size_t row) const { return rows_[row].off; }
+    uint32_t row_length(size_t row) const { return rows_[row].len; }
+    // Hands the file image over (the table's accessors are dead afterwards).
+    std::string take_data() { return std::move(data_); }
 
     // Worker threads used for parsing / filtering large tables (1 for small inputs).
     static unsigned worker_threads(size_t bytes);

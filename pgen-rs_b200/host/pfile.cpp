@@ -175,41 +175,53 @@ VcfPlan Pfile::plan_vcf(const std::optional<std::string> &sam_query, const std::
         }
         h.push_back('\n');
 
-        // line prefixes, pfile.rs:157-161: every field + '\t', then "GT".  Without csv quoting a
-        // record's fields joined by '\t' are its text in the file, so one copy per kept row.
+        // line prefixes, pfile.rs:157-161: every field + '\t', then "GT".  Without csv quoting a record's fields
+        // joined by '\t' are its text in the file, so the device copies the row from the raw image and appends
+        // "\tGT"; the host only records where each kept row sits.
         const size_t nv = plan.var_idx.size();
-        plan.prefix_off.resize(nv + 1);
-        uint64_t total = 0;
+        plan.row_off.resize(nv);
+        plan.row_len.resize(nv);
         for (size_t k = 0; k < nv; k++) {
-            plan.prefix_off[k] = total;
-            total += pvar.row_text(plan.var_idx[k]).size() + 3;
+            plan.row_off[k] = pvar.row_offset(plan.var_idx[k]);
+            plan.row_len[k] = pvar.row_length(plan.var_idx[k]);
         }
-        plan.prefix_off[nv] = total;
-        plan.prefix_blob.resize(total);
-        uint8_t *base = plan.prefix_blob.data();
-        const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(nv, MetaTable::worker_threads(total)));
-        auto fill = [&](unsigned t) {
-            const size_t a = nv / T * t, b = t + 1 == T ? nv : nv / T * (t + 1);
-            for (size_t k = a; k < b; k++) {
-                const std::string_view r = pvar.row_text(plan.var_idx[k]);
-                uint8_t *w = base + plan.prefix_off[k];
-                memcpy(w, r.data(), r.size());
-                w += r.size();
-                w[0] = '\t';
-                w[1] = 'G';
-                w[2] = 'T';
-            }
-        };
-        if (T == 1) fill(0);
-        else {
-            std::vector<std::thread> th;
-            for (unsigned t = 0; t < T; t++) th.emplace_back(fill, t);
-            for (auto &x : th) x.join();
-        }
+        plan.pvar_text = pvar.take_data();
     } catch (const MetaError &e) {
         throw PfileError{e.status, e.msg};
     }
     return plan;
+}
+
+void VcfPlan::materialize_prefixes() {
+    const size_t nv = var_idx.size();
+    if (prefix_off.size() == nv + 1) return;
+    prefix_off.resize(nv + 1);
+    uint64_t total = 0;
+    for (size_t k = 0; k < nv; k++) {
+        prefix_off[k] = total;
+        total += (uint64_t)row_len[k] + 3;
+    }
+    prefix_off[nv] = total;
+    prefix_blob.resize(total);
+    uint8_t *base = prefix_blob.data();
+    const unsigned T = (unsigned)std::max<size_t>(1, std::min<size_t>(nv, MetaTable::worker_threads(total)));
+    auto fill = [&](unsigned t) {
+        const size_t a = nv / T * t, b = t + 1 == T ? nv : nv / T * (t + 1);
+        for (size_t k = a; k < b; k++) {
+            uint8_t *w = base + prefix_off[k];
+            memcpy(w, pvar_text.data() + row_off[k], row_len[k]);
+            w += row_len[k];
+            w[0] = '\t';
+            w[1] = 'G';
+            w[2] = 'T';
+        }
+    };
+    if (T == 1) fill(0);
+    else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; t++) th.emplace_back(fill, t);
+        for (auto &x : th) x.join();
+    }
 }
 
 void Pfile::output_vcf(const std::optional<std::string> &sam_query, const std::optional<std::string> &var_query,
@@ -228,8 +240,9 @@ void Pfile::output_vcf(const std::optional<std::string> &sam_query, const std::o
     // an empty std::vector may hand out nullptr, which the C ABI reads as "all samples"
     static const uint32_t no_samples[1] = {0};
     const uint32_t *sam = plan.sam_idx.empty() ? no_samples : plan.sam_idx.data();
-    rc = pgb_export_gt_vcf(f, plan.var_idx.data(), plan.var_idx.size(), sam, plan.sam_idx.size(),
-                           plan.prefix_blob.data(), plan.prefix_off.data(), fd, device_ids, n_devices, stats);
+    rc = pgb_export_gt_vcf_rows(f, plan.var_idx.data(), plan.var_idx.size(), sam, plan.sam_idx.size(),
+                                (const uint8_t *)plan.pvar_text.data(), plan.pvar_text.size(), plan.row_off.data(),
+                                plan.row_len.data(), fd, device_ids, n_devices, stats);
     std::string detail = pgb_last_error();
     pgb_close(f);
     if (rc != PGB_OK) throw PfileError{rc, std::string(pgb_strerror(rc)) + ": " + detail};

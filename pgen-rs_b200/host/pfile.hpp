@@ -29,8 +29,15 @@ std::vector<uint32_t> filter_metadata(MetaTable &table, const std::optional<std:
 struct VcfPlan {
     std::vector<uint32_t> var_idx, sam_idx;
     std::string header;              // pfile.rs:139-146
-    std::vector<uint8_t> prefix_blob; // pfile.rs:157-161 per kept variant, concatenated
-    std::vector<uint64_t> prefix_off; // n_var + 1
+    // The line prefixes (pfile.rs:157-161) are built on the device: the plan only carries the raw .pvar image
+    // and, per kept variant, where its row sits in it.
+    std::string pvar_text;
+    std::vector<uint64_t> row_off;
+    std::vector<uint32_t> row_len;
+    // The finished prefixes as a blob + n_var + 1 offsets (what pgb_export_gt_vcf takes); built only on demand.
+    void materialize_prefixes();
+    std::vector<uint8_t> prefix_blob;
+    std::vector<uint64_t> prefix_off;
 };
 
 class Pfile {

@@ -78,6 +78,9 @@ SYMBOLS = {
     "pgb_export_gt_vcf": (_i, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _i, _vp, _i, C.POINTER(Stats)]),
     "pgb_export_gt_vcf_mem": (_i, [_vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _u64, C.POINTER(_u64), _vp, _i,
                                    C.POINTER(Stats)]),
+    "pgb_export_gt_vcf_rows": (_i, [_vp, _vp, _u64, _vp, _u64, _vp, _u64, _vp, _vp, _i, _vp, _i, C.POINTER(Stats)]),
+    "pgb_export_gt_vcf_rows_mem": (_i, [_vp, _vp, _u64, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _u64, C.POINTER(_u64), _vp, _i,
+                                        C.POINTER(Stats)]),
     "pgb_release_buffers": (None, []),
     "pgb_body_bytes": (_u64, [_u64, _u64, _vp]),
     "pgb_shard_plan": (_i, [_u64, _u64, _vp, _i, _vp, _vp]),
@@ -90,6 +93,9 @@ SYMBOLS = {
     "pgb_plan_var_idx": (_vp, [_vp]),
     "pgb_plan_sam_idx": (_vp, [_vp]),
     "pgb_plan_header": (_vp, [_vp, C.POINTER(_u64)]),
+    "pgb_plan_pvar_text": (_vp, [_vp, C.POINTER(_u64)]),
+    "pgb_plan_row_off": (_vp, [_vp]),
+    "pgb_plan_row_len": (_vp, [_vp]),
     "pgb_plan_prefix_blob": (_vp, [_vp, C.POINTER(_u64)]),
     "pgb_plan_prefix_off": (_vp, [_vp]),
     "pgb_pgen10_index": (_i, [C.c_char_p, C.POINTER(Pgen10Info), _vp, _vp, _vp]),
@@ -200,6 +206,25 @@ class PgenFile:
         return n_out.value, st
 
 
+def export_rows_to_bytes(f: PgenFile, var_idx, sam_idx, pvar_text: np.ndarray, row_off, row_len, devices=None) -> bytes:
+    """pgb_export_gt_vcf_rows_mem: prefixes built on the device from the raw .pvar image."""
+    vi, si = _u32arr(var_idx), _u32arr(sam_idx)
+    ro = np.ascontiguousarray(row_off, dtype=np.uint64)
+    rl = np.ascontiguousarray(row_len, dtype=np.uint32)
+    tx = np.ascontiguousarray(pvar_text, dtype=np.uint8)
+    k = f.n_samples if sam_idx is None else len(sam_idx)
+    total = int(rl.astype(np.uint64).sum()) + len(rl) * (3 + 4 * k + 1)
+    out = np.empty(max(total, 1), dtype=np.uint8)
+    dv = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+    st = Stats()
+    n_out = _u64()
+    rc = lib.pgb_export_gt_vcf_rows_mem(f.h, _ptr(vi), len(rl), _sam_ptr(si), 0 if si is None else len(si), _ptr(tx), tx.nbytes,
+                                        _ptr(ro), _ptr(rl), out.ctypes.data, total, C.byref(n_out), _ptr(dv),
+                                        0 if dv is None else len(dv), C.byref(st))
+    _check(rc, "pgb_export_gt_vcf_rows_mem")
+    return out[:n_out.value].tobytes()
+
+
 def export_to_bytes(f: PgenFile, var_idx, sam_idx, prefix_blob, prefix_off, devices=None) -> bytes:
     po = np.ascontiguousarray(prefix_off, dtype=np.uint64)
     k = f.n_samples if sam_idx is None else len(sam_idx)
@@ -231,6 +256,10 @@ class VcfPlan:
             self.var_idx = np.ctypeslib.as_array(C.cast(lib.pgb_plan_var_idx(h), C.POINTER(_u32)), (nv,)).copy() if nv else np.zeros(0, np.uint32)
             self.sam_idx = np.ctypeslib.as_array(C.cast(lib.pgb_plan_sam_idx(h), C.POINTER(_u32)), (ns,)).copy() if ns else np.zeros(0, np.uint32)
             ln = _u64()
+            p = lib.pgb_plan_pvar_text(h, C.byref(ln))
+            self.pvar_text = np.frombuffer(C.string_at(p, ln.value), dtype=np.uint8).copy() if ln.value else np.zeros(0, np.uint8)
+            self.row_off = np.ctypeslib.as_array(C.cast(lib.pgb_plan_row_off(h), C.POINTER(_u64)), (nv,)).copy() if nv else np.zeros(0, np.uint64)
+            self.row_len = np.ctypeslib.as_array(C.cast(lib.pgb_plan_row_len(h), C.POINTER(_u32)), (nv,)).copy() if nv else np.zeros(0, np.uint32)
             p = lib.pgb_plan_header(h, C.byref(ln))
             self.header = C.string_at(p, ln.value)
             p = lib.pgb_plan_prefix_blob(h, C.byref(ln))

@@ -610,3 +610,36 @@ def test_logical_shards_on_one_gpu_concatenate(pgb):
                 parts.append(pgb.export_to_bytes(f, var[a:b], sam, blob, sub_off) if b > a else b"")
                 assert len(parts[-1]) == int(bb[g + 1] - bb[g])
             assert b"".join(parts) == whole
+
+
+def test_prefixes_built_on_the_device_from_raw_pvar_rows(pgb, monkeypatch):
+    """pgb_export_gt_vcf_rows: the line prefix is the row as it is in the .pvar image + "\\tGT" appended by K2
+    (pfile.rs:157-161); dense selections DMA the covering text range, sparse ones pack the kept rows, and the
+    caller's row order is kept.  Checked against the oracle's grammar on a made-up .pvar with \\n and \\r\\n
+    terminators, empty lines and rows of 1 to 300 bytes."""
+    rng = np.random.default_rng(123)
+    n, m = 911, 4000
+    recs = rng.integers(0, 256, size=(m, synth.record_size(n)), dtype=np.uint8)
+    rows = [bytes(rng.integers(33, 127, size=int(rng.integers(1, 301)), dtype=np.uint8)) for _ in range(m)]
+    text = b"##comment\n#CHROM\tPOS\n"
+    off = np.zeros(m, np.uint64)
+    for i, r in enumerate(rows):
+        off[i] = len(text)
+        text += r + [b"\n", b"\r\n", b"\n\n"][i % 3]
+    ln = np.array([len(r) for r in rows], np.uint32)
+    tx = np.frombuffer(text, dtype=np.uint8)
+    sam = np.sort(rng.choice(n, size=150, replace=False)).astype(np.uint32)
+    with pgb.PgenFile(image=image_of(recs, n)) as f:
+        for chunk_mb in ("128", "1"):
+            monkeypatch.setenv("PGB_CHUNK_MB", chunk_mb)
+            for var in (np.arange(m, dtype=np.uint32), np.sort(rng.choice(m, size=m // 2, replace=False)).astype(np.uint32),
+                        np.sort(rng.choice(m, size=9, replace=False)).astype(np.uint32), rng.permutation(m)[:700].astype(np.uint32),
+                        np.zeros(0, np.uint32)):
+                for sel in (None, sam, np.zeros(0, np.uint32)):
+                    got = pgb.export_rows_to_bytes(f, var, sel, tx, off[var], ln[var])
+                    want = onp.format_body(recs, var, np.arange(n) if sel is None else sel, [rows[v] + b"\tGT" for v in var])
+                    assert got == want, (chunk_mb, len(var), None if sel is None else len(sel))
+        # a row outside the image is refused
+        with pytest.raises(pgb.PgbError) as ei:
+            pgb.export_rows_to_bytes(f, [0], None, tx, np.array([len(text) - 2], np.uint64), np.array([5], np.uint32))
+        assert ei.value.status == pgb.E_RANGE

@@ -90,6 +90,11 @@ def test_plan_basic1_config1(pgb, basic1):
     assert plan.prefix_blob.tobytes() == exp
     assert int(plan.prefix_off[-1]) == len(exp)
     assert pgb.lib.pgb_body_bytes(len(vi), 1, plan.prefix_off.ctypes.data) == 706753
+    # what output_vcf hands to the device instead of the blob: the raw .pvar image and the kept rows in it
+    assert plan.pvar_text.tobytes() == pvar
+    for k in (0, 1, 77, len(vi) - 1):
+        a, n = int(plan.row_off[k]), int(plan.row_len[k])
+        assert pvar[a:a + n] + b"\tGT" == onp.line_prefix(vrows[vi[k]])
 
 
 def test_plan_keep_all(pgb, basic1):
