@@ -751,6 +751,8 @@ def run_b200(args, wl, rank, world, local_rank):
                 ceil = file_sink_ceilings(path + ".probe", mv, n_thr)
                 best = max([v for v in ceil.values() if isinstance(v, float)] or [0.0])
                 agg_best = sum_over_ranks(best)
+                od_rate = ceil.get("o_direct_pwrite_%d" % n_thr)
+                agg_od = sum_over_ranks(od_rate if isinstance(od_rate, float) else 0.0)
                 ts = []
                 for it in range(3):
                     fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
@@ -773,7 +775,7 @@ def run_b200(args, wl, rank, world, local_rank):
                                      "peak_source": "best raw sink rate of the same bytes without the GPU, all ranks at once, measured in this "
                                                     "run: max over {1 buffered pwrite thread, N buffered pwrite threads, N O_DIRECT pwrite "
                                                     "threads, N copies through a MAP_SHARED mapping}, N = %d per rank" % n_thr,
-                                     "rank0_sink_rates_gbs": ceil}}
+                                     "rank0_sink_rates_gbs": ceil, "o_direct_ceiling_gbs_all_ranks": agg_od}}
             finally:
                 for q in (path, path + ".probe"):
                     if os.path.exists(q):
@@ -786,6 +788,17 @@ def run_b200(args, wl, rank, world, local_rank):
             disk = tempfile.gettempdir()
             if os.path.isdir(disk) and os.stat(disk).st_dev != os.stat(shm).st_dev:
                 e2e_file_disk = file_leg(disk, "block-device file system, page cache")
+                if e2e_file_disk is not None:
+                    os.environ["PGB_ODIRECT"] = "1"  # the opt-in O_DIRECT output stage on the same file system
+                    try:
+                        od = file_leg(disk, "block-device file system, O_DIRECT output stage (PGB_ODIRECT=1)")
+                    finally:
+                        del os.environ["PGB_ODIRECT"]
+                    e2e_file_disk["o_direct_variant"] = None if od is None else dict(
+                        {k: od[k] for k in ("value", "vcf_gb_per_s", "ms_per_step", "sink")},
+                        parallel_o_direct_ceiling_gbs=od["roofline"]["o_direct_ceiling_gbs_all_ranks"],
+                        frac_of_parallel_o_direct_ceiling=(od["vcf_gb_per_s"] / od["roofline"]["o_direct_ceiling_gbs_all_ranks"]
+                                                           if od["roofline"]["o_direct_ceiling_gbs_all_ranks"] else None))
     clocks = sampler.stop() if sampler else None
 
     # ---- configs[4] (biobank shape), strong scaling + the product's own multi-device call ----

@@ -221,6 +221,7 @@ struct Sink {
     bool mem_pinned = false;
     WritePool *pool = nullptr; // positional sinks only
     uint8_t *map = nullptr;    // regular-file sink mapped MAP_SHARED: map[0] is file offset `base`
+    int dfd = -1;              // the same file opened O_DIRECT (PGB_ODIRECT=1): 4 KiB-aligned interiors bypass the page cache
     // ordered (non-positional) writes
     std::mutex mu;
     std::condition_variable cv;
@@ -295,7 +296,7 @@ int ensure_slot(Slot &s, uint64_t need_in, uint64_t need_out, uint64_t need_line
         CU(cudaMalloc((void **)&s.d_out, cap));
         s.cap_out = cap;
     }
-    if (need_h_out && !s.h_out) CU(cudaHostAlloc((void **)&s.h_out, s.cap_out, cudaHostAllocDefault));
+    if (need_h_out && !s.h_out) CU(cudaHostAlloc((void **)&s.h_out, s.cap_out + 4096, cudaHostAllocDefault));
     if (need_lines > s.cap_lines) {
         if (s.d_meta) cudaFree(s.d_meta);
         if (s.d_scratch) cudaFree(s.d_scratch);
@@ -440,6 +441,7 @@ Stage stage_layout(const Job &j, const Chunk &c, bool records_inline) {
 struct Pending {
     int slot;
     size_t chunk;
+    uint32_t shift; // the chunk sits at h_out + shift: file offset and memory address agree modulo 4 KiB (O_DIRECT)
 };
 
 void writer_loop(Job *job, DeviceWork *w, std::deque<Pending> *q, std::mutex *qmu, std::condition_variable *qcv,
@@ -477,6 +479,21 @@ void writer_loop(Job *job, DeviceWork *w, std::deque<Pending> *q, std::mutex *qm
                 // to one inode serialise on its lock (measured: 4-5 GB/s however many threads)
                 if (sk->pool) rc = sk->pool->write(-1, s.h_out, ch.out_bytes, (uint64_t)(uintptr_t)(sk->map + ch.out_off));
                 else memcpy(sk->map + ch.out_off, s.h_out, ch.out_bytes);
+            } else if (sk->positional && sk->dfd >= 0) {
+                // O_DIRECT output stage: the 4 KiB-aligned interior of the chunk goes from the page-locked slot straight
+                // to the device queue (file offset, memory address and length all 4 KiB-aligned); the ragged ends
+                // (shared 4 KiB blocks with the neighbouring chunks) go through the page cache
+                const uint8_t *src = s.h_out + p.shift;
+                const uint64_t fo = sk->base + ch.out_off, fe = fo + ch.out_bytes;
+                const uint64_t a0 = align_up(fo, 4096), a1 = fe / 4096 * 4096;
+                if (a0 < a1) {
+                    rc = write_fully(sk->fd, src, a0 - fo, true, fo);
+                    if (!rc) rc = sk->pool ? sk->pool->write(sk->dfd, src + (a0 - fo), a1 - a0, a0)
+                                           : write_fully(sk->dfd, src + (a0 - fo), a1 - a0, true, a0);
+                    if (!rc) rc = write_fully(sk->fd, src + (a1 - fo), fe - a1, true, a1);
+                } else {
+                    rc = write_fully(sk->fd, src, ch.out_bytes, true, fo);
+                }
             } else if (sk->positional) {
                 rc = sk->pool ? sk->pool->write(sk->fd, s.h_out, ch.out_bytes, sk->base + ch.out_off)
                               : write_fully(sk->fd, s.h_out, ch.out_bytes, true, sk->base + ch.out_off);
@@ -653,14 +670,15 @@ int run_device_inner(Job *job, DeviceWork *w, std::deque<Pending> &q, std::mutex
         if (rc) return rc;
         CU(cudaEventRecord(s.ev_k1, st));
         w->launches += 4;
-        uint8_t *dst = need_h_out ? s.h_out : job->sink->mem + ch.out_off;
+        const uint32_t shift = job->sink->dfd >= 0 ? (uint32_t)((job->sink->base + ch.out_off) & 4095u) : 0u;
+        uint8_t *dst = need_h_out ? s.h_out + shift : job->sink->mem + ch.out_off;
         CU(cudaMemcpyAsync(dst, s.d_out, ch.out_bytes, cudaMemcpyDeviceToHost, st));
         w->d2h += ch.out_bytes;
         CU(cudaEventRecord(s.ev_done, st));
         job->lap("enqueued", ci);
         {
             std::lock_guard<std::mutex> lk(qmu);
-            q.push_back(Pending{si, ci});
+            q.push_back(Pending{si, ci, shift});
         }
         qcv.notify_one();
     }
@@ -911,7 +929,15 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
             // for pwrite(); on ext4 the mapping's write faults make it slower (2 vs 4.7 GB/s) -> tmpfs only.
             struct statfs sfs;
             const bool tmpfs = fstatfs(sink->fd, &sfs) == 0 && (unsigned long)sfs.f_type == 0x01021994ul;
-            if (regular && total >= (64u << 20) && env_u64("PGB_MMAP_SINK", tmpfs ? 1 : 0)) {
+            // O_DIRECT output stage (opt-in, PGB_ODIRECT=1): measured on this pool's boxes (virtio disk, ext4) it is
+            // slower than page-cache writes that never reach the disk inside the call (3.9 vs 5.5 GB/s, profiles/README.md);
+            // on a box whose page cache cannot hold the VCF it is the path that keeps the export off the cache
+            if (regular && !tmpfs && total >= (8u << 20) && env_u64("PGB_ODIRECT", 0)) {
+                char link[64];
+                snprintf(link, sizeof link, "/proc/self/fd/%d", sink->fd);
+                sink->dfd = open(link, O_WRONLY | O_DIRECT);
+            }
+            if (sink->dfd < 0 && regular && total >= (64u << 20) && env_u64("PGB_MMAP_SINK", tmpfs ? 1 : 0)) {
                 // map the body region; the caller's descriptor is usually write-only (File::create), which
                 // mmap(PROT_WRITE, MAP_SHARED) rejects, so reopen the same file read-write through /proc
                 char link[64];
@@ -945,8 +971,12 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
         for (auto &t : th) t.join();
     }
     lap("devices done");
-    sink->pool = nullptr; // both die with this call
+    sink->pool = nullptr; // all three die with this call
     sink->map = nullptr;
+    if (sink->dfd >= 0) {
+        close(sink->dfd);
+        sink->dfd = -1;
+    }
     int rc = job.status.load();
     if (rc != PGB_OK) {
         pgb_set_error("%s", job.err);

@@ -140,6 +140,18 @@ def test_chunking_slots_and_sinks(pgb, tmp_path, monkeypatch):
         os.write(fd, b"TAIL")
         os.close(fd)
         assert open(out, "rb").read() == b"HEADER\n" + want + b"TAIL"
+        # the same through the O_DIRECT output stage (4 KiB-aligned interiors straight from the page-locked slots,
+        # ragged ends buffered); falls back silently where the file system refuses O_DIRECT
+        monkeypatch.setenv("PGB_ODIRECT", "1")
+        for hdr in (b"HEADER\n", b"", b"x" * 4096, b"y" * 5000):
+            out = str(tmp_path / "direct.vcf")
+            fd = os.open(out, os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+            os.write(fd, hdr)
+            f.export_gt_vcf(None, None, blob, off, fd)
+            assert os.lseek(fd, 0, os.SEEK_CUR) == len(hdr) + len(want)
+            os.close(fd)
+            assert open(out, "rb").read() == hdr + want
+        monkeypatch.delenv("PGB_ODIRECT")
         out = str(tmp_path / "app.vcf")
         open(out, "wb").write(b"H\n")
         fd = os.open(out, os.O_WRONLY | os.O_APPEND)
