@@ -62,19 +62,27 @@ struct pgb_k2b_params {
     uint32_t stages;     // input stages (records, prefixes, table): 2 or 3
 };
 
+#if defined(PGB_HOSTSIM)
+#define PGB_HD static inline
+#define PGB_HDM inline
+#else
+#define PGB_HD __host__ __device__ __forceinline__
+#define PGB_HDM __host__ __device__ __forceinline__
+#endif
+
 // Shared memory: [0,64) the mbarriers (full[s] at 8 s: a stage's copies have landed; empty[s] at 32 + 8 s: the
 // consumer warps are done with a stage), the text table, then per stage s a table (16 bytes per consumer warp: body offset and
 // image byte range of the warp's lines; 32 bytes per line, see k2b_produce), the staged records and prefixes;
 // the gather plan; one virtual record per consumer warp; two images (each one part per consumer warp).
 struct pgb_k2b_layout {
-    uint32_t lut, tab[3], rows[3], pst[3], plan, vrec, outb[2], total;
+    uint32_t lut, tab0, tabsz, rows0, rowsz, pst0, pstsz, plan, vrec, outb0, outsz, total;
+    // offsets of stage s / image i (plain arithmetic: indexing an array member with a run-time stage would put
+    // the struct in local memory)
+    PGB_HDM uint32_t tab(uint32_t s) const { return tab0 + s * tabsz; }
+    PGB_HDM uint32_t rows(uint32_t s) const { return rows0 + s * rowsz; }
+    PGB_HDM uint32_t pst(uint32_t s) const { return pst0 + s * pstsz; }
+    PGB_HDM uint32_t outb(uint32_t i) const { return outb0 + i * outsz; }
 };
-
-#if defined(PGB_HOSTSIM)
-#define PGB_HD static inline
-#else
-#define PGB_HD __host__ __device__ __forceinline__
-#endif
 
 PGB_HD uint32_t pgb_k2b_align(uint32_t x, uint32_t a) { return (x + a - 1u) & ~(a - 1u); }
 
@@ -82,16 +90,17 @@ PGB_HD pgb_k2b_layout pgb_k2b_smem_layout(uint32_t B, uint32_t rowcap, uint32_t 
                                           bool gather, uint32_t images = 2, uint32_t stages = 2) {
     pgb_k2b_layout L;
     L.lut = 64;
-    const uint32_t tabsz = K2B_TAB_LINES + 32u * B;
-    uint32_t o = L.lut + 128;
-    for (uint32_t s = 0; s < 3; s++) { L.tab[s] = o; if (s < stages) o += tabsz; }
-    for (uint32_t s = 0; s < 3; s++) { L.rows[s] = o; if (s < stages) o += B * rowcap; }
-    for (uint32_t s = 0; s < 3; s++) { L.pst[s] = o; if (s < stages) o += B * pcap; }
-    L.plan = o;
+    L.tabsz = K2B_TAB_LINES + 32u * B;
+    L.rowsz = B * rowcap;
+    L.pstsz = B * pcap;
+    L.tab0 = L.lut + 128;
+    L.rows0 = L.tab0 + stages * L.tabsz;
+    L.pst0 = L.rows0 + stages * L.rowsz;
+    L.plan = L.pst0 + stages * L.pstsz;
     L.vrec = L.plan + (gather ? vcap * 16u : 0u); // 16 bytes of plan per virtual-record byte (vcap >= ceil(K/4))
-    L.outb[0] = pgb_k2b_align(L.vrec + (gather ? K2B_WARPS * vcap : 0u), 128);
-    L.outb[1] = images > 1 ? L.outb[0] + outcap : L.outb[0];
-    L.total = L.outb[1] + outcap;
+    L.outb0 = pgb_k2b_align(L.vrec + (gather ? K2B_WARPS * vcap : 0u), 128);
+    L.outsz = images > 1 ? outcap : 0u;
+    L.total = L.outb0 + (images > 1 ? 2u : 1u) * outcap;
     return L;
 }
 
@@ -181,7 +190,7 @@ PGB_DEV void k2b_produce(const pgb_k2b_params &p, uint8_t *smem, const pgb_k2b_l
                          uint32_t lane, const pgb_line_meta &m, uint64_t first_off, uint64_t next_off, uint64_t base,
                          uint64_t end_off, uint64_t pfx0, bool packed, uint32_t span_lo, uint32_t span_len) {
     uint8_t *mbar = smem + 8u * stage;
-    uint8_t *tab = smem + L.tab[stage];
+    uint8_t *tab = smem + L.tab(stage);
     const uint8_t *p0 = p.prefix_blob + pfx0;
     const uint32_t pph0 = (uint32_t)(uintptr_t)p0 & 15u;
     uint8_t *pdst = nullptr;
@@ -191,7 +200,7 @@ PGB_DEV void k2b_produce(const pgb_k2b_params &p, uint8_t *smem, const pgb_k2b_l
         // all prefix bytes of the batch: its size minus the GT text, newlines and suffixes
         const uint32_t D = (uint32_t)(end_off - base) - nbl * (4u * p.K + 1u + p.sfx_len);
         if (packed && D) {
-            pdst = smem + L.pst[stage];
+            pdst = smem + L.pst(stage);
             psrc = p0 - pph0;
             pbytes = (pph0 + D + 15u) & ~15u;
         }
@@ -224,20 +233,20 @@ PGB_DEV void k2b_produce(const pgb_k2b_params &p, uint8_t *smem, const pgb_k2b_l
         const uint32_t pph = dlen ? (uint32_t)(uintptr_t)q & 15u : 0u;
         pst_off = lane * p.pcap + pph;
         if (dlen) {
-            pdst = smem + L.pst[stage] + lane * p.pcap;
+            pdst = smem + L.pst(stage) + lane * p.pcap;
             psrc = q - pph;
             pbytes = (pph + dlen + 15u) & ~15u;
         }
     }
     d[0] = o_ls;
     d[1] = dlen;
-    d[2] = L.pst[stage] + pst_off;
+    d[2] = L.pst(stage) + pst_off;
     d[3] = o_ge;
-    d[4] = L.rows[stage] + lane * p.rowcap + ph;
+    d[4] = L.rows(stage) + lane * p.rowcap + ph;
     d[5] = o_gs;
     d[6] = (o_gs + 15u) & ~15u;
     d[7] = o_ge & ~15u;
-    k2b_stage_load(mbar, smem + L.rows[stage] + lane * p.rowcap, src - ph, span_len ? (ph + span_len + 15u) & ~15u : 0u, pdst,
+    k2b_stage_load(mbar, smem + L.rows(stage) + lane * p.rowcap, src - ph, span_len ? (ph + span_len + 15u) & ~15u : 0u, pdst,
                    psrc, pbytes);
 }
 
@@ -279,14 +288,14 @@ PGB_DEV uint32_t k2b_gt_byte(const uint8_t *vrec, const uint8_t *lut, uint32_t g
 template <bool GATHER>
 PGB_DEV void k2b_line_gather(const pgb_k2b_params &p, uint8_t *smem, const pgb_k2b_layout &L, uint32_t stage, uint32_t img,
                              uint32_t l, uint32_t warp, uint32_t lane) {
-    const pgb_u4 d = pgb_lds4(reinterpret_cast<const pgb_u4 *>(smem + L.tab[stage] + K2B_TAB_LINES + 32u * l));
-    uint8_t *outb = smem + L.outb[img];
+    const pgb_u4 d = pgb_lds4(reinterpret_cast<const pgb_u4 *>(smem + L.tab(stage) + K2B_TAB_LINES + 32u * l));
+    uint8_t *outb = smem + L.outb(img);
     const uint8_t *src = smem + d.z;
     for (uint32_t x = lane; x < d.y; x += 32) outb[d.x + x] = src[x];
     if (lane < p.sfx_len) outb[d.x + d.y + lane] = (uint8_t)(p.sfx >> (8u * lane));
     if (lane == 31) outb[d.w] = '\n';
     if (!GATHER) return;
-    const uint8_t *row = smem + reinterpret_cast<const uint32_t *>(smem + L.tab[stage] + K2B_TAB_LINES + 32u * l)[4];
+    const uint8_t *row = smem + reinterpret_cast<const uint32_t *>(smem + L.tab(stage) + K2B_TAB_LINES + 32u * l)[4];
     const uint32_t nb = (p.K + 3u) >> 2;
     uint8_t *vrec = smem + L.vrec + warp * p.vcap;
     const pgb_u4 *plan = reinterpret_cast<const pgb_u4 *>(smem + L.plan);
@@ -302,9 +311,9 @@ PGB_DEV void k2b_line_gather(const pgb_k2b_params &p, uint8_t *smem, const pgb_k
 template <bool GATHER>
 PGB_DEV void k2b_line_format(const pgb_k2b_params &p, uint8_t *smem, const pgb_k2b_layout &L, uint32_t stage, uint32_t img,
                              uint32_t l, uint32_t warp, uint32_t lane) {
-    const pgb_u4 d = pgb_lds4(reinterpret_cast<const pgb_u4 *>(smem + L.tab[stage] + K2B_TAB_LINES + 16u + 32u * l));
+    const pgb_u4 d = pgb_lds4(reinterpret_cast<const pgb_u4 *>(smem + L.tab(stage) + K2B_TAB_LINES + 16u + 32u * l));
     const uint8_t *lut = smem + L.lut;
-    uint8_t *outb = smem + L.outb[img];
+    uint8_t *outb = smem + L.outb(img);
     const uint8_t *vrec = GATHER ? smem + L.vrec + warp * p.vcap : smem + d.x;
     const uint32_t o_gs = d.y, b0 = d.z, b1 = d.w;
     if (b0 >= b1) { // no aligned chunk inside the text: byte by byte

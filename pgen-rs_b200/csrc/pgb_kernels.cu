@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2_batch_kernel(const pgb_k2b_par
             else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
         k2b_mbar_wait(smem + 8u * stage, par); // table written, records and prefixes landed
-        const pgb_u4 h = pgb_lds4(reinterpret_cast<const pgb_u4 *>(smem + L.tab[stage] + 16u * warp));
+        const pgb_u4 h = pgb_lds4(reinterpret_cast<const pgb_u4 *>(smem + L.tab(stage) + 16u * warp));
         __syncwarp();
         const uint32_t l1 = (warp + 1u) * LPW < nbl ? (warp + 1u) * LPW : nbl;
         for (uint32_t l = warp * LPW; l < l1; l++) {
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(K2B_THREADS) k2_batch_kernel(const pgb_k2b_par
         if (lane == 0) k2b_arrive(smem + 32u + 8u * stage);
         if (++stage == p.stages) { stage = 0; par ^= 1u; }
         const uint32_t ws = h.z, we = h.w;
-        const uint8_t *outb = smem + L.outb[img];
+        const uint8_t *outb = smem + L.outb(img);
         const uint64_t g_al = (uint64_t)(uintptr_t)p.out + (((uint64_t)h.y << 32) | h.x) - ws;
         if (ws != 0xFFFFFFFFu) {
             const uint32_t h0 = (ws + 15u) & ~15u, h1 = we & ~15u;
@@ -658,14 +658,10 @@ static int launch_k2(const pgb_k2_params &p, cudaStream_t st) {
                           : launch_k2_one<GATHER, HINT, REPL, IPW, false>(p, st);
 }
 
+// Items per warp: 1 or 4 (the two values the launcher's defaults use; other requests round to the nearer one).
 template <bool GATHER, int HINT, int REPL>
 static int launch_k2_ipw(const pgb_k2_params &p, cudaStream_t st, int ipw) {
-    switch (ipw) {
-    case 1: return launch_k2<GATHER, HINT, REPL, 1>(p, st);
-    case 2: return launch_k2<GATHER, HINT, REPL, 2>(p, st);
-    case 8: return launch_k2<GATHER, HINT, REPL, 8>(p, st);
-    default: return launch_k2<GATHER, HINT, REPL, 4>(p, st);
-    }
+    return ipw >= 3 ? launch_k2<GATHER, HINT, REPL, 4>(p, st) : launch_k2<GATHER, HINT, REPL, 1>(p, st);
 }
 
 // Batch path (k2_batch.cuh): plan the shared-memory budget; returns false when the lines are too long for it.
@@ -724,9 +720,9 @@ static int launch_k2_batch(pgb_k2b_params &bp, uint32_t smem_bytes, int variant,
     return check_launch("k2_batch_kernel");
 }
 
-// variant: bits 0-3   store hint (0 => .cs streaming, the measured best; 2 => default write-back)
+// variant: bits 0-3   (ignored; was the store hint: .cs streaming stores are always used)
 //          bits 4-7   LUT copies (0 => default, see below; 1 => 8 interleaved bank-conflict-free copies; 2 => one)
-//          bits 8-11  items per warp (0 => default; 1, 2, 4, 8)
+//          bits 8-11  items per warp (0 => default; 1-2 => 1, 3 and more => 4)
 //          bits 12-15 tile size = 4 KiB << n (0 => 16 KiB)
 //          bits 16-19 batch path (k2_batch.cuh): 0 => default (gather launches whose batch fits), 1 => off, 2 => on
 //                     whenever the batch fits (also keep-all)
@@ -794,13 +790,12 @@ extern "C" int pgb_dev_format_lines_ex(const uint8_t *records, uint32_t record_b
     // bytes of a record worth prefetching: all of it for keep-all, up to the last kept sample otherwise
     p.row_bytes_hint = kidx ? 0u : (n_kept + 3u) / 4u + 1u;
     p.kidx_vec = kidx_vec;
+    // 16 instantiations: {keep-all, gather} x {8, 1 LUT copies} x {1, 4 items per warp} x {whole lines, tiles}; all
+    // use .cs streaming stores (the default write-back variant measured 4 % slower in round 1 and was dropped)
+    (void)hint;
     const bool g = gatherp;
-    if (hint == 1) {
-        if (repl8) return g ? launch_k2_ipw<true, 1, 8>(p, st, ipw) : launch_k2_ipw<false, 1, 8>(p, st, ipw);
-        return g ? launch_k2_ipw<true, 1, 1>(p, st, ipw) : launch_k2_ipw<false, 1, 1>(p, st, ipw);
-    }
-    if (repl8) return g ? launch_k2_ipw<true, 0, 8>(p, st, ipw) : launch_k2_ipw<false, 0, 8>(p, st, ipw);
-    return g ? launch_k2_ipw<true, 0, 1>(p, st, ipw) : launch_k2_ipw<false, 0, 1>(p, st, ipw);
+    if (repl8) return g ? launch_k2_ipw<true, 1, 8>(p, st, ipw) : launch_k2_ipw<false, 1, 8>(p, st, ipw);
+    return g ? launch_k2_ipw<true, 1, 1>(p, st, ipw) : launch_k2_ipw<false, 1, 1>(p, st, ipw);
 }
 
 extern "C" int pgb_dev_format_lines(const uint8_t *records, const pgb_line_meta *meta, uint64_t n_lines,

@@ -115,7 +115,7 @@ extern "C" int sim_format_lines_batch(const uint8_t *records, uint64_t pitch, ui
             issue(bt + (uint64_t)(p.stages - 1) * grid, (n + p.stages - 1) % p.stages);
             for (uint32_t warp = 0; warp < K2B_WARPS; warp++) {
                 uint32_t h[4];
-                memcpy(h, smem + L.tab[stage] + 16u * warp, 16);
+                memcpy(h, smem + L.tab(stage) + 16u * warp, 16);
                 const uint32_t l1 = (warp + 1u) * LPW < nbl ? (warp + 1u) * LPW : nbl;
                 for (uint32_t l = warp * LPW; l < l1; l++) {
                     for (uint32_t lane = 0; lane < 32; lane++) {
@@ -132,7 +132,7 @@ extern "C" int sim_format_lines_batch(const uint8_t *records, uint64_t pitch, ui
                 if (ws == 0xFFFFFFFFu) continue;
                 const uint64_t g_al = (uint64_t)(uintptr_t)p.out + (((uint64_t)h[1] << 32) | h[0]) - ws;
                 if (g_al & 15u) return -1;
-                const uint8_t *outb = smem + L.outb[img];
+                const uint8_t *outb = smem + L.outb(img);
                 const uint32_t h0 = (ws + 15u) & ~15u, h1 = we & ~15u;
                 if (h0 < h1) memcpy((void *)(uintptr_t)(g_al + h0), outb + h0, h1 - h0); // the warp's bulk store
                 for (uint32_t lane = 0; lane < 32; lane++) k2b_store_edges(g_al, outb, ws, we, lane);
