@@ -58,7 +58,8 @@ struct pgb_k2b_params {
     uint32_t sfx_len;  // 0..4; pfx_len includes it
     uint32_t kidx_vec; // kidx is 16-byte aligned
     uint32_t store_mode; // 0 bulk async store, 1 16-byte st.global by all threads (A/B comparisons)
-    uint32_t images;     // 2: a warp formats batch n+1 while its store of batch n drains; 1: it waits for the drain
+    uint32_t images;     // 0: no image — the consumer warps store to global memory directly; 1: an image per warp,
+                         // bulk-stored (the warp waits for the drain before the next batch); 2: two images per warp
     uint32_t stages;     // input stages (records, prefixes, table): 2 or 3
 };
 
@@ -100,7 +101,7 @@ PGB_HD pgb_k2b_layout pgb_k2b_smem_layout(uint32_t B, uint32_t rowcap, uint32_t 
     L.vrec = L.plan + (gather ? vcap * 16u : 0u); // 16 bytes of plan per virtual-record byte (vcap >= ceil(K/4))
     L.outb0 = pgb_k2b_align(L.vrec + (gather ? K2B_WARPS * vcap : 0u), 128);
     L.outsz = images > 1 ? outcap : 0u;
-    L.total = L.outb0 + (images > 1 ? 2u : 1u) * outcap;
+    L.total = L.outb0 + images * outcap;
     return L;
 }
 
@@ -275,6 +276,13 @@ PGB_DEV void k2b_build_plan(const pgb_k2b_params &p, uint8_t *smem, const pgb_k2
     }
 }
 
+// One byte of a virtual record from the staged record span and the byte's plan entry.
+PGB_DEV uint32_t k2b_compact_byte(const uint8_t *row, const pgb_u4 &e) {
+    const uint32_t acc = (pgb_funnel_l(0u, row[e.x >> 5], e.x) & 0x00C0u) | (pgb_funnel_l(0u, row[e.y >> 5], e.y) & 0x0300u) |
+                         (pgb_funnel_l(0u, row[e.z >> 5], e.z) & 0x0C00u) | (pgb_funnel_l(0u, row[e.w >> 5], e.w) & 0x3000u);
+    return acc >> 6;
+}
+
 // One byte of a line's GT text from its (virtual) record: g = offset from the start of the text.
 PGB_DEV uint32_t k2b_gt_byte(const uint8_t *vrec, const uint8_t *lut, uint32_t g) {
     const uint32_t f = g >> 2;
@@ -282,35 +290,51 @@ PGB_DEV uint32_t k2b_gt_byte(const uint8_t *vrec, const uint8_t *lut, uint32_t g
     return lut[code * 8u + (g & 3u)]; // table entry `code`: the text word of genotype `code` comes first
 }
 
+// Where a consumer warp puts its text: its part of the shared-memory image (IMG; the image leaves by bulk store),
+// or global memory directly (16-byte .cs stores for the aligned chunks, byte stores for prefixes and ragged ends).
+// Offsets are image offsets in both cases; `g_al` is the global address of image offset 0 (16-byte aligned).
+template <bool IMG>
+PGB_DEV void k2b_put8(uint8_t *outb, uint64_t g_al, uint32_t off, uint32_t v) {
+    if (IMG) outb[off] = (uint8_t)v;
+    else pgb_st8(g_al + off, v);
+}
+template <bool IMG>
+PGB_DEV void k2b_put16(uint8_t *outb, uint64_t g_al, uint32_t off, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    if (IMG) k2b_sts16(outb + off, x, y, z, w);
+    else pgb_st16(g_al + off, x, y, z, w, 1);
+}
+
 // ---- CONSUMER, one line, first half (a warp per line, no CTA-wide synchronisation): prefix bytes
-//      (pfile.rs:157-161) and the newline (pfile.rs:190) into the image; GATHER (pfile.rs:171-175): lane <->
-//      bytes lane, lane + 32, ... of the warp's virtual record, 4 LDS.U8 + shift/mask per byte. ----
-template <bool GATHER>
+//      (pfile.rs:157-161) and the newline (pfile.rs:190); GATHER (pfile.rs:171-175): lane <-> bytes lane,
+//      lane + 32, ... of the warp's virtual record, 4 LDS.U8 + shift/mask per byte.  `preg0` / `preg1`: the lane's
+//      plan entries for bytes lane and lane + 32, held in registers for the whole kernel when ceil(K/4) <= 64. ----
+template <bool GATHER, bool IMG>
 PGB_DEV void k2b_line_gather(const pgb_k2b_params &p, uint8_t *smem, const pgb_k2b_layout &L, uint32_t stage, uint32_t img,
-                             uint32_t l, uint32_t warp, uint32_t lane) {
+                             uint64_t g_al, uint32_t l, uint32_t warp, uint32_t lane, const pgb_u4 &preg0,
+                             const pgb_u4 &preg1) {
     const pgb_u4 d = pgb_lds4(reinterpret_cast<const pgb_u4 *>(smem + L.tab(stage) + K2B_TAB_LINES + 32u * l));
     uint8_t *outb = smem + L.outb(img);
     const uint8_t *src = smem + d.z;
-    for (uint32_t x = lane; x < d.y; x += 32) outb[d.x + x] = src[x];
-    if (lane < p.sfx_len) outb[d.x + d.y + lane] = (uint8_t)(p.sfx >> (8u * lane));
-    if (lane == 31) outb[d.w] = '\n';
+    for (uint32_t x = lane; x < d.y; x += 32) k2b_put8<IMG>(outb, g_al, d.x + x, src[x]);
+    if (lane < p.sfx_len) k2b_put8<IMG>(outb, g_al, d.x + d.y + lane, (p.sfx >> (8u * lane)) & 0xFFu);
+    if (lane == 31) k2b_put8<IMG>(outb, g_al, d.w, '\n');
     if (!GATHER) return;
     const uint8_t *row = smem + reinterpret_cast<const uint32_t *>(smem + L.tab(stage) + K2B_TAB_LINES + 32u * l)[4];
     const uint32_t nb = (p.K + 3u) >> 2;
     uint8_t *vrec = smem + L.vrec + warp * p.vcap;
     const pgb_u4 *plan = reinterpret_cast<const pgb_u4 *>(smem + L.plan);
-    for (uint32_t j = lane; j < nb; j += 32) {
-        const pgb_u4 e = pgb_lds4(plan + j);
-        const uint32_t acc = (pgb_funnel_l(0u, row[e.x >> 5], e.x) & 0x00C0u) | (pgb_funnel_l(0u, row[e.y >> 5], e.y) & 0x0300u) |
-                             (pgb_funnel_l(0u, row[e.z >> 5], e.z) & 0x0C00u) | (pgb_funnel_l(0u, row[e.w >> 5], e.w) & 0x3000u);
-        vrec[j] = (uint8_t)(acc >> 6);
+    if (nb <= 64u) { // the whole plan is in registers: bytes lane and lane + 32
+        if (lane < nb) vrec[lane] = (uint8_t)k2b_compact_byte(row, preg0);
+        if (lane + 32u < nb) vrec[lane + 32u] = (uint8_t)k2b_compact_byte(row, preg1);
+        return;
     }
+    for (uint32_t j = lane; j < nb; j += 32) vrec[j] = (uint8_t)k2b_compact_byte(row, pgb_lds4(plan + j));
 }
 
-// ---- CONSUMER, one line, second half: FORMAT (pfile.rs:177-188) — the GT text into the image ----
-template <bool GATHER>
+// ---- CONSUMER, one line, second half: FORMAT (pfile.rs:177-188) — the GT text ----
+template <bool GATHER, bool IMG>
 PGB_DEV void k2b_line_format(const pgb_k2b_params &p, uint8_t *smem, const pgb_k2b_layout &L, uint32_t stage, uint32_t img,
-                             uint32_t l, uint32_t warp, uint32_t lane) {
+                             uint64_t g_al, uint32_t l, uint32_t warp, uint32_t lane) {
     const pgb_u4 d = pgb_lds4(reinterpret_cast<const pgb_u4 *>(smem + L.tab(stage) + K2B_TAB_LINES + 16u + 32u * l));
     const uint8_t *lut = smem + L.lut;
     uint8_t *outb = smem + L.outb(img);
@@ -318,7 +342,7 @@ PGB_DEV void k2b_line_format(const pgb_k2b_params &p, uint8_t *smem, const pgb_k
     const uint32_t o_gs = d.y, b0 = d.z, b1 = d.w;
     if (b0 >= b1) { // no aligned chunk inside the text: byte by byte
         const uint32_t K4 = 4u * p.K;
-        for (uint32_t g = lane; g < K4; g += 32) outb[o_gs + g] = (uint8_t)k2b_gt_byte(vrec, lut, g);
+        for (uint32_t g = lane; g < K4; g += 32) k2b_put8<IMG>(outb, g_al, o_gs + g, k2b_gt_byte(vrec, lut, g));
         return;
     }
     const uint32_t delta = b0 - o_gs; // (A - o_gs) & 15 for any 16-aligned A
@@ -328,13 +352,13 @@ PGB_DEV void k2b_line_format(const pgb_k2b_params &p, uint8_t *smem, const pgb_k
         const uint32_t w = pgb_prmt(vp[0], vp[1], 0x1140u) >> sh; // 10 code bits: 5 fields
         const pgb_u2 e01 = k2b_lds8(lut + ((w & 15u) << 3)), e23 = k2b_lds8(lut + ((w & 0xF0u) >> 1));
         const uint32_t W4 = pgb_prmt(0x2E313030u, 0x00002F09u, ((w >> 4) & 0x30u) | 0x0504u);
-        k2b_sts16(outb + A, pgb_funnel_r(e01.x, e01.y, r8), pgb_funnel_r(e01.y, e23.x, r8), pgb_funnel_r(e23.x, e23.y, r8),
-                  pgb_funnel_r(e23.y, W4, r8));
+        k2b_put16<IMG>(outb, g_al, A, pgb_funnel_r(e01.x, e01.y, r8), pgb_funnel_r(e01.y, e23.x, r8),
+                       pgb_funnel_r(e23.x, e23.y, r8), pgb_funnel_r(e23.y, W4, r8));
     }
     // <= 15 bytes of text in front of the first chunk (lanes 0-15) and behind the last one (lanes 16-31)
     const uint32_t x = lane < 16 ? o_gs + lane : b1 + (lane - 16u);
     const uint32_t end = lane < 16 ? b0 : o_gs + 4u * p.K;
-    if (x < end) outb[x] = (uint8_t)k2b_gt_byte(vrec, lut, x - o_gs);
+    if (x < end) k2b_put8<IMG>(outb, g_al, x, k2b_gt_byte(vrec, lut, x - o_gs));
 }
 
 // The 16-entry text table: nibble -> the text words of its two genotypes.

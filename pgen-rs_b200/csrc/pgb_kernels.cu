@@ -320,15 +320,16 @@ __device__ __forceinline__ void k2b_mbar_wait(uint8_t *mbar, uint32_t parity) {
     const uint32_t bar = k2b_smem_addr(mbar);
     uint32_t done;
     do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        // the suspend-time hint lets the hardware park the warp instead of spinning in the issue slots
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done)
-                     : "r"(bar), "r"(parity)
+                     : "r"(bar), "r"(parity), "r"(20000u)
                      : "memory");
     } while (!done);
 }
 
-template <bool GATHER>
-__global__ void __launch_bounds__(K2B_THREADS) k2_batch_kernel(const pgb_k2b_params p) {
+template <bool GATHER, bool IMG>
+__global__ void __launch_bounds__(K2B_THREADS, 3) k2_batch_kernel(const pgb_k2b_params p) {
     extern __shared__ __align__(128) uint8_t k2b_smem[];
     uint8_t *smem = k2b_smem;
     const pgb_k2b_layout L = pgb_k2b_smem_layout(p.B, p.rowcap, p.pcap, p.vcap, p.outcap, GATHER, p.images, p.stages);
@@ -407,6 +408,16 @@ __global__ void __launch_bounds__(K2B_THREADS) k2_batch_kernel(const pgb_k2b_par
     // ---------------------------------------------------- consumer warps ----
     // Warp w formats lines [w * LPW, (w + 1) * LPW) of every batch into its own part of the image and stores that
     // contiguous byte range itself: the consumer warps never wait for one another.
+    // the lane's gather plan for bytes lane and lane + 32 of a virtual record, in registers when that is all of it
+    pgb_u4 preg0 = {0u, 0u, 0u, 0u}, preg1 = preg0;
+    if (GATHER) {
+        const uint32_t nb = (p.K + 3u) >> 2;
+        const pgb_u4 *plan = reinterpret_cast<const pgb_u4 *>(smem + L.plan);
+        if (nb <= 64u) {
+            if (lane < nb) preg0 = pgb_lds4(plan + lane);
+            if (lane + 32u < nb) preg1 = pgb_lds4(plan + lane + 32u);
+        }
+    }
     uint32_t bt = blockIdx.x;
     for (uint32_t n = 0, stage = 0, par = 0;; n++, bt += gridDim.x) {
         const uint32_t nbl = lines_of(bt);
@@ -414,49 +425,53 @@ __global__ void __launch_bounds__(K2B_THREADS) k2_batch_kernel(const pgb_k2b_par
         const uint32_t img = p.images > 1 ? n & 1u : 0u;
         // the part of the image this warp is about to rewrite (batch n-2's, or n-1's with a single image) must have
         // left shared memory
-        if (lane == 0) {
+        if (IMG && lane == 0) {
             if (p.images > 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
         k2b_mbar_wait(smem + 8u * stage, par); // table written, records and prefixes landed
         const pgb_u4 h = pgb_lds4(reinterpret_cast<const pgb_u4 *>(smem + L.tab(stage) + 16u * warp));
         __syncwarp();
+        const uint32_t ws = h.z, we = h.w;
+        const uint64_t g_al = (uint64_t)(uintptr_t)p.out + (((uint64_t)h.y << 32) | h.x) - ws;
         const uint32_t l1 = (warp + 1u) * LPW < nbl ? (warp + 1u) * LPW : nbl;
         for (uint32_t l = warp * LPW; l < l1; l++) {
-            k2b_line_gather<GATHER>(p, smem, L, stage, img, l, warp, lane);
+            k2b_line_gather<GATHER, IMG>(p, smem, L, stage, img, g_al, l, warp, lane, preg0, preg1);
             if (GATHER) __syncwarp();
-            k2b_line_format<GATHER>(p, smem, L, stage, img, l, warp, lane);
+            k2b_line_format<GATHER, IMG>(p, smem, L, stage, img, g_al, l, warp, lane);
             if (GATHER) __syncwarp();
         }
-        // the image was written through the generic proxy; the bulk store reads it through the async proxy
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (IMG) {
+            // the image was written through the generic proxy; the bulk store reads it through the async proxy
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
         __syncwarp();
         // this warp no longer reads the stage's table, records or prefixes: let the producer refill it
         if (lane == 0) k2b_arrive(smem + 32u + 8u * stage);
         if (++stage == p.stages) { stage = 0; par ^= 1u; }
-        const uint32_t ws = h.z, we = h.w;
-        const uint8_t *outb = smem + L.outb(img);
-        const uint64_t g_al = (uint64_t)(uintptr_t)p.out + (((uint64_t)h.y << 32) | h.x) - ws;
-        if (ws != 0xFFFFFFFFu) {
-            const uint32_t h0 = (ws + 15u) & ~15u, h1 = we & ~15u;
-            if (p.store_mode == 0) {
-                if (lane == 0 && h0 < h1)
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g_al + h0),
-                                 "r"(k2b_smem_addr(outb + h0)), "r"(h1 - h0)
-                                 : "memory");
-            } else {
-                for (uint32_t a = h0 + 16u * lane; a < h1; a += 512u) {
-                    const uint4 v = *reinterpret_cast<const uint4 *>(outb + a);
-                    pgb_st16(g_al + a, v.x, v.y, v.z, v.w, 1);
+        if (IMG) {
+            const uint8_t *outb = smem + L.outb(img);
+            if (ws != 0xFFFFFFFFu) {
+                const uint32_t h0 = (ws + 15u) & ~15u, h1 = we & ~15u;
+                if (p.store_mode == 0) {
+                    if (lane == 0 && h0 < h1)
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g_al + h0),
+                                     "r"(k2b_smem_addr(outb + h0)), "r"(h1 - h0)
+                                     : "memory");
+                } else {
+                    for (uint32_t a = h0 + 16u * lane; a < h1; a += 512u) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(outb + a);
+                        pgb_st16(g_al + a, v.x, v.y, v.z, v.w, 1);
+                    }
                 }
+                k2b_store_edges(g_al, outb, ws, we, lane);
             }
-            k2b_store_edges(g_al, outb, ws, we, lane);
+            // one group per batch (possibly empty), so that wait_group.read 1 means "batch n-2 has left"
+            if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        // one group per batch (possibly empty), so that wait_group.read 1 means "batch n-2 has left"
-        if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     // shared memory must stay intact until the last bulk stores have read it
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (IMG && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // -------------------------------------------------------------- synth ------
@@ -675,7 +690,7 @@ static bool plan_k2_batch(uint32_t K, uint32_t R, bool gather, uint32_t max_pref
     const uint64_t vcap = gather ? (((uint64_t)(K + 3u) / 4ull + 2ull + 15ull) & ~15ull) : 0ull;
     // measured on the gather-heavy chr22 shape (profiles/README.md): one image per warp and two input stages with
     // 24 lines per batch beat two images / three stages with the 16 lines those leave room for
-    const uint64_t images = ((variant >> 29) & 1) ? 2 : 1, stages = ((variant >> 30) & 1) ? 3 : 2;
+    const uint64_t images = ((variant >> 28) & 1) ? 0 : ((variant >> 29) & 1) ? 2 : 1, stages = ((variant >> 30) & 1) ? 3 : 2;
     const uint64_t per_line = stages * (rowcap + pcap + 32ull) + images * max_line;
     const uint64_t fixed = 64 + 128 + stages * 128 + 128 + images * K2B_WARPS * 160 + vcap * 16 + vcap * K2B_WARPS;
     if (budget <= fixed + 2 * per_line) return false;
@@ -690,23 +705,23 @@ static bool plan_k2_batch(uint32_t K, uint32_t R, bool gather, uint32_t max_pref
     bp->rowcap = (uint32_t)rowcap;
     bp->pcap = (uint32_t)pcap;
     bp->vcap = (uint32_t)vcap;
-    bp->wcap = (uint32_t)((k2b_lines_per_warp((uint32_t)B) * max_line + 32ull + 127ull) & ~127ull);
+    bp->wcap = images ? (uint32_t)((k2b_lines_per_warp((uint32_t)B) * max_line + 32ull + 127ull) & ~127ull) : 0u;
     bp->outcap = K2B_WARPS * bp->wcap;
-    bp->store_mode = (variant >> 28) & 1;
+    bp->store_mode = 0;
     bp->images = (uint32_t)images;
     bp->stages = (uint32_t)stages;
     *smem_bytes = pgb_k2b_smem_layout(bp->B, bp->rowcap, bp->pcap, bp->vcap, bp->outcap, gather, bp->images, bp->stages).total;
     return *smem_bytes <= 227u * 1024u;
 }
 
-template <bool GATHER>
+template <bool GATHER, bool IMG>
 static int launch_k2_batch(pgb_k2b_params &bp, uint32_t smem_bytes, int variant, cudaStream_t st) {
     const uint64_t batches = (bp.n_lines + bp.B - 1) / bp.B;
     if (bp.n_lines > 0xffffffffull) return PGB_E_ARG;
     bp.n_batches = (uint32_t)batches;
-    cudaError_t e = cudaFuncSetAttribute(k2_batch_kernel<GATHER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(k2_batch_kernel<GATHER, IMG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     int per_sm = 0, dev = 0, sms = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_batch_kernel<GATHER>, K2B_THREADS, smem_bytes);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k2_batch_kernel<GATHER, IMG>, K2B_THREADS, smem_bytes);
     if (e == cudaSuccess) e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess || per_sm < 1 || sms < 1) {
@@ -716,7 +731,7 @@ static int launch_k2_batch(pgb_k2b_params &bp, uint32_t smem_bytes, int variant,
     const uint64_t grid0 = (uint64_t)per_sm * (uint64_t)sms; // persistent grid: every SM full
     uint64_t grid = grid0;
     if (grid > batches) grid = batches;
-    k2_batch_kernel<GATHER><<<(unsigned)grid, K2B_THREADS, smem_bytes, st>>>(bp);
+    k2_batch_kernel<GATHER, IMG><<<(unsigned)grid, K2B_THREADS, smem_bytes, st>>>(bp);
     return check_launch("k2_batch_kernel");
 }
 
@@ -728,7 +743,7 @@ static int launch_k2_batch(pgb_k2b_params &bp, uint32_t smem_bytes, int variant,
 //                     whenever the batch fits (also keep-all)
 //          bits 20-23 batch path: lines per batch <= 2 * n (0 => up to 32)
 //          bits 24-27 batch path: shared-memory budget = n * 16 KiB (0 => 72 KiB, three CTAs per SM)
-//          bit  28    batch path: 16-byte st.global stores instead of the bulk async store
+//          bit  28    batch path: no shared-memory image: the consumer warps store to global memory directly
 //          bit  29    batch path: two output images per warp instead of one
 //          bit  30    batch path: three input stages instead of two
 extern "C" int pgb_dev_format_lines_ex(const uint8_t *records, uint32_t record_bytes, const pgb_line_meta *meta,
@@ -759,7 +774,11 @@ extern "C" int pgb_dev_format_lines_ex(const uint8_t *records, uint32_t record_b
             bp.sfx = suffix;
             bp.sfx_len = suffix_len;
             bp.kidx_vec = kidx_vec;
-            return gatherp ? launch_k2_batch<true>(bp, smem_bytes, variant, st) : launch_k2_batch<false>(bp, smem_bytes, variant, st);
+            if (bp.images)
+                return gatherp ? launch_k2_batch<true, true>(bp, smem_bytes, variant, st)
+                               : launch_k2_batch<false, true>(bp, smem_bytes, variant, st);
+            return gatherp ? launch_k2_batch<true, false>(bp, smem_bytes, variant, st)
+                           : launch_k2_batch<false, false>(bp, smem_bytes, variant, st);
         }
     }
     pgb_k2_params p;

@@ -63,13 +63,13 @@ extern "C" int sim_format_lines_batch(const uint8_t *records, uint64_t pitch, ui
     p.pcap = pgb_k2b_align(maxp - (maxp < sfx_len ? maxp : sfx_len) + 31u, 16);
     p.vcap = gather ? pgb_k2b_align((K + 3u) / 4u + 2u, 16) : 0u;
     const uint64_t max_line = (uint64_t)maxp + 4ull * K + 1ull;
-    p.wcap = pgb_k2b_align((uint32_t)(k2b_lines_per_warp(B) * max_line + 32u), 128);
+    p.images = (flags & 16) ? 0u : (flags & 4) ? 1u : 2u;
+    p.wcap = p.images ? pgb_k2b_align((uint32_t)(k2b_lines_per_warp(B) * max_line + 32u), 128) : 0u;
     p.outcap = K2B_WARPS * p.wcap;
     p.sfx = sfx;
     p.sfx_len = sfx_len;
     p.kidx_vec = (flags & 1) ? 1u : 0u;
     p.store_mode = 0;
-    p.images = (flags & 4) ? 1u : 2u;
     p.stages = (flags & 8) ? 3u : 2u;
     const pgb_k2b_layout L = pgb_k2b_smem_layout(p.B, p.rowcap, p.pcap, p.vcap, p.outcap, gather, p.images, p.stages);
     std::vector<uint8_t> smem_store(L.total + 256);
@@ -116,22 +116,39 @@ extern "C" int sim_format_lines_batch(const uint8_t *records, uint64_t pitch, ui
             for (uint32_t warp = 0; warp < K2B_WARPS; warp++) {
                 uint32_t h[4];
                 memcpy(h, smem + L.tab(stage) + 16u * warp, 16);
+                const uint32_t ws = h[2], we = h[3];
+                if ((ws == 0xFFFFFFFFu) != (warp * LPW >= nbl)) return -2;
+                const uint64_t g_al = (uint64_t)(uintptr_t)p.out + (((uint64_t)h[1] << 32) | h[0]) - ws;
+                if (ws != 0xFFFFFFFFu && (g_al & 15u)) return -1;
+                const uint32_t nb = (K + 3u) >> 2;
                 const uint32_t l1 = (warp + 1u) * LPW < nbl ? (warp + 1u) * LPW : nbl;
                 for (uint32_t l = warp * LPW; l < l1; l++) {
                     for (uint32_t lane = 0; lane < 32; lane++) {
-                        if (gather) k2b_line_gather<true>(p, smem, L, stage, img, l, warp, lane);
-                        else k2b_line_gather<false>(p, smem, L, stage, img, l, warp, lane);
+                        pgb_u4 preg[2] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};
+                        if (gather && nb <= 64u) {
+                            const pgb_u4 *plan = reinterpret_cast<const pgb_u4 *>(smem + L.plan);
+                            if (lane < nb) preg[0] = plan[lane];
+                            if (lane + 32u < nb) preg[1] = plan[lane + 32u];
+                        }
+                        if (gather) {
+                            if (p.images) k2b_line_gather<true, true>(p, smem, L, stage, img, g_al, l, warp, lane, preg[0], preg[1]);
+                            else k2b_line_gather<true, false>(p, smem, L, stage, img, g_al, l, warp, lane, preg[0], preg[1]);
+                        } else {
+                            if (p.images) k2b_line_gather<false, true>(p, smem, L, stage, img, g_al, l, warp, lane, preg[0], preg[1]);
+                            else k2b_line_gather<false, false>(p, smem, L, stage, img, g_al, l, warp, lane, preg[0], preg[1]);
+                        }
                     }
                     for (uint32_t lane = 0; lane < 32; lane++) {
-                        if (gather) k2b_line_format<true>(p, smem, L, stage, img, l, warp, lane);
-                        else k2b_line_format<false>(p, smem, L, stage, img, l, warp, lane);
+                        if (gather) {
+                            if (p.images) k2b_line_format<true, true>(p, smem, L, stage, img, g_al, l, warp, lane);
+                            else k2b_line_format<true, false>(p, smem, L, stage, img, g_al, l, warp, lane);
+                        } else {
+                            if (p.images) k2b_line_format<false, true>(p, smem, L, stage, img, g_al, l, warp, lane);
+                            else k2b_line_format<false, false>(p, smem, L, stage, img, g_al, l, warp, lane);
+                        }
                     }
                 }
-                const uint32_t ws = h[2], we = h[3];
-                if ((ws == 0xFFFFFFFFu) != (warp * LPW >= nbl)) return -2;
-                if (ws == 0xFFFFFFFFu) continue;
-                const uint64_t g_al = (uint64_t)(uintptr_t)p.out + (((uint64_t)h[1] << 32) | h[0]) - ws;
-                if (g_al & 15u) return -1;
+                if (ws == 0xFFFFFFFFu || !p.images) continue;
                 const uint8_t *outb = smem + L.outb(img);
                 const uint32_t h0 = (ws + 15u) & ~15u, h1 = we & ~15u;
                 if (h0 < h1) memcpy((void *)(uintptr_t)(g_al + h0), outb + h0, h1 - h0); // the warp's bulk store

@@ -134,7 +134,7 @@ def run_sim_batch(k2sim, rng, n, m, k_sel, var_sel, plen, phase, B, sfx=b"", kid
     else:
         rc = k2sim.sim_format_lines_batch(flat.ctypes.data, r, r, vptr, len(vr), blob.ctypes.data, off.ctypes.data,
                                           None if ki is None else ki.ctypes.data, k, buf.ctypes.data + start, B,
-                                          sfx_word, len(sfx), kidx_vec | (2 if unpacked else 0) | (4 if phase % 3 == 0 else 0) | (8 if phase % 5 < 2 else 0))
+                                          sfx_word, len(sfx), kidx_vec | (2 if unpacked else 0) | (4 if phase % 3 == 0 else 0) | (8 if phase % 5 < 2 else 0) | (16 if phase % 2 else 0))
     assert rc == 0
     got = buf[start:start + len(exp)].tobytes()
     if got != exp:
