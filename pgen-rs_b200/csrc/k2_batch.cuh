@@ -315,7 +315,12 @@ PGB_DEV void k2b_line_gather(const pgb_k2b_params &p, uint8_t *smem, const pgb_k
     const pgb_u4 d = pgb_lds4(reinterpret_cast<const pgb_u4 *>(smem + L.tab(stage) + K2B_TAB_LINES + 32u * l));
     uint8_t *outb = smem + L.outb(img);
     const uint8_t *src = smem + d.z;
-    for (uint32_t x = lane; x < d.y; x += 32) k2b_put8<IMG>(outb, g_al, d.x + x, src[x]);
+    for (uint32_t x = lane; x < d.y; x += 64) { // two bytes per lane and iteration: both loads before the stores
+        const bool two = x + 32u < d.y;
+        const uint32_t b0 = src[x], b1 = two ? src[x + 32u] : 0u;
+        k2b_put8<IMG>(outb, g_al, d.x + x, b0);
+        if (two) k2b_put8<IMG>(outb, g_al, d.x + x + 32u, b1);
+    }
     if (lane < p.sfx_len) k2b_put8<IMG>(outb, g_al, d.x + d.y + lane, (p.sfx >> (8u * lane)) & 0xFFu);
     if (lane == 31) k2b_put8<IMG>(outb, g_al, d.w, '\n');
     if (!GATHER) return;
@@ -348,12 +353,21 @@ PGB_DEV void k2b_line_format(const pgb_k2b_params &p, uint8_t *smem, const pgb_k
     const uint32_t delta = b0 - o_gs; // (A - o_gs) & 15 for any 16-aligned A
     const uint32_t r8 = (delta & 3u) * 8u, sh = (delta >> 2) * 2u;
     const uint8_t *vp = vrec + lane;
-    for (uint32_t A = b0 + 16u * lane; A < b1; A += 512u, vp += 32) {
-        const uint32_t w = pgb_prmt(vp[0], vp[1], 0x1140u) >> sh; // 10 code bits: 5 fields
+    // two chunks per lane and iteration (512 bytes apart): their loads are issued together, so a warp has two
+    // independent LDS -> ALU -> LDS -> ALU -> store chains in flight instead of one
+    for (uint32_t A = b0 + 16u * lane; A < b1; A += 1024u, vp += 64) {
+        const bool two = A + 512u < b1;
+        const uint32_t a0 = vp[0], a1 = vp[1], c0 = two ? vp[32] : 0u, c1 = two ? vp[33] : 0u;
+        const uint32_t w = pgb_prmt(a0, a1, 0x1140u) >> sh, v = pgb_prmt(c0, c1, 0x1140u) >> sh; // 10 code bits: 5 fields
         const pgb_u2 e01 = k2b_lds8(lut + ((w & 15u) << 3)), e23 = k2b_lds8(lut + ((w & 0xF0u) >> 1));
+        const pgb_u2 f01 = k2b_lds8(lut + ((v & 15u) << 3)), f23 = k2b_lds8(lut + ((v & 0xF0u) >> 1));
         const uint32_t W4 = pgb_prmt(0x2E313030u, 0x00002F09u, ((w >> 4) & 0x30u) | 0x0504u);
+        const uint32_t V4 = pgb_prmt(0x2E313030u, 0x00002F09u, ((v >> 4) & 0x30u) | 0x0504u);
         k2b_put16<IMG>(outb, g_al, A, pgb_funnel_r(e01.x, e01.y, r8), pgb_funnel_r(e01.y, e23.x, r8),
                        pgb_funnel_r(e23.x, e23.y, r8), pgb_funnel_r(e23.y, W4, r8));
+        if (two)
+            k2b_put16<IMG>(outb, g_al, A + 512u, pgb_funnel_r(f01.x, f01.y, r8), pgb_funnel_r(f01.y, f23.x, r8),
+                           pgb_funnel_r(f23.x, f23.y, r8), pgb_funnel_r(f23.y, V4, r8));
     }
     // <= 15 bytes of text in front of the first chunk (lanes 0-15) and behind the last one (lanes 16-31)
     const uint32_t x = lane < 16 ? o_gs + lane : b1 + (lane - 16u);

@@ -329,7 +329,7 @@ __device__ __forceinline__ void k2b_mbar_wait(uint8_t *mbar, uint32_t parity) {
 }
 
 template <bool GATHER, bool IMG>
-__global__ void __launch_bounds__(K2B_THREADS, 3) k2_batch_kernel(const pgb_k2b_params p) {
+__global__ void __launch_bounds__(K2B_THREADS, IMG ? 3 : 4) k2_batch_kernel(const pgb_k2b_params p) {
     extern __shared__ __align__(128) uint8_t k2b_smem[];
     uint8_t *smem = k2b_smem;
     const pgb_k2b_layout L = pgb_k2b_smem_layout(p.B, p.rowcap, p.pcap, p.vcap, p.outcap, GATHER, p.images, p.stages);
