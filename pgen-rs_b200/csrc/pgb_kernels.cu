@@ -329,7 +329,7 @@ __device__ __forceinline__ void k2b_mbar_wait(uint8_t *mbar, uint32_t parity) {
 }
 
 template <bool GATHER, bool IMG>
-__global__ void __launch_bounds__(K2B_THREADS, IMG ? 3 : 4) k2_batch_kernel(const pgb_k2b_params p) {
+__global__ void __launch_bounds__(K2B_THREADS, 3) k2_batch_kernel(const pgb_k2b_params p) {
     extern __shared__ __align__(128) uint8_t k2b_smem[];
     uint8_t *smem = k2b_smem;
     const pgb_k2b_layout L = pgb_k2b_smem_layout(p.B, p.rowcap, p.pcap, p.vcap, p.outcap, GATHER, p.images, p.stages);
@@ -688,9 +688,14 @@ static bool plan_k2_batch(uint32_t K, uint32_t R, bool gather, uint32_t max_pref
     const uint64_t rowcap = ((uint64_t)R + 31ull + 15ull) & ~15ull;
     const uint64_t pcap = ((uint64_t)(max_prefix_len - std::min(max_prefix_len, suffix_len)) + 31ull + 15ull) & ~15ull;
     const uint64_t vcap = gather ? (((uint64_t)(K + 3u) / 4ull + 2ull + 15ull) & ~15ull) : 0ull;
-    // measured on the gather-heavy chr22 shape (profiles/README.md): one image per warp and two input stages with
-    // 24 lines per batch beat two images / three stages with the 16 lines those leave room for
-    const uint64_t images = ((variant >> 28) & 1) ? 0 : ((variant >> 29) & 1) ? 2 : 1, stages = ((variant >> 30) & 1) ? 3 : 2;
+    // Measured (profiles/README.md).  Gather-heavy chr22 shape: the consumer warps storing to global memory directly
+    // with three input stages of 24 lines (0.178 ms) beat one bulk-stored shared-memory image per warp with two
+    // stages (0.186 ms: the image's 1 KB per line costs a third of the lines a batch can hold).  Keep-all lines of
+    // 1.2-2.4 KB (records of 75-150 bytes, so the image is nearly all of the batch): the image wins, 0.276 / 0.322 /
+    // 0.463 ms against 0.310 / 0.398 / 0.564 ms direct for 300 / 400 / 600 samples x 1 M variants.
+    const int isel = (variant >> 28) & 3;
+    const uint64_t images = isel == 1 ? 1 : isel == 2 ? 2 : isel == 3 ? 0 : (gather ? 0 : 1);
+    const uint64_t stages = (((variant >> 30) & 1) != 0) == gather ? 2 : 3;
     const uint64_t per_line = stages * (rowcap + pcap + 32ull) + images * max_line;
     const uint64_t fixed = 64 + 128 + stages * 128 + 128 + images * K2B_WARPS * 160 + vcap * 16 + vcap * K2B_WARPS;
     if (budget <= fixed + 2 * per_line) return false;
@@ -743,9 +748,10 @@ static int launch_k2_batch(pgb_k2b_params &bp, uint32_t smem_bytes, int variant,
 //                     whenever the batch fits (also keep-all)
 //          bits 20-23 batch path: lines per batch <= 2 * n (0 => up to 32)
 //          bits 24-27 batch path: shared-memory budget = n * 16 KiB (0 => 72 KiB, three CTAs per SM)
-//          bit  28    batch path: no shared-memory image: the consumer warps store to global memory directly
-//          bit  29    batch path: two output images per warp instead of one
-//          bit  30    batch path: three input stages instead of two
+//          bits 28-29 batch path: 3 => the consumer warps store to global memory directly (default for gather); 1 / 2 =>
+//                     one / two shared-memory images per warp, bulk-stored with cp.async.bulk.global.shared::cta
+//                     (1 is the default for keep-all)
+//          bit  30    batch path: the other number of input stages (default: three for gather, two for keep-all)
 extern "C" int pgb_dev_format_lines_ex(const uint8_t *records, uint32_t record_bytes, const pgb_line_meta *meta,
                                        uint64_t n_lines, const uint8_t *prefix_blob, uint32_t suffix, uint32_t suffix_len,
                                        const uint32_t *kidx, uint32_t n_kept, uint32_t max_prefix_len, uint8_t *out,

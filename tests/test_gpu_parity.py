@@ -54,10 +54,11 @@ def test_golden_vectors_through_pfile_api(pgb, kat_cases, tmp_path):
         assert open(out, "rb").read() == case["vcf"].encode(), case["name"]
 
 
-# bits 16-27 steer the batch path (k2_batch.cuh): 0x1.... off, 0x2.... on for keep-all too, smaller batches / budgets,
-# 0x1....... plain stores instead of the bulk async store
+# bits 16-30 steer the batch path (k2_batch.cuh): 0x1.... off, 0x2.... on for keep-all too, smaller batches / budgets,
+# 0x1....... / 0x2....... one / two bulk-stored shared-memory images per warp, 0x3....... direct stores,
+# 0x4....... the other number of input stages
 @pytest.mark.parametrize("variant", [0x000, 0x010, 0x020, 0x112, 0x222, 0x1410, 0x2822, 0x10000, 0x20000, 0x10220000,
-                                     0x02120000, 0x07020000])
+                                     0x02120000, 0x07020000, 0x20020000, 0x50420000, 0x30020000])
 def test_random_shapes_bit_exact(pgb, variant, monkeypatch):
     monkeypatch.setenv("PGB_K2_VARIANT", str(variant))
     rng = np.random.default_rng(variant + 5)
