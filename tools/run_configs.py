@@ -1,7 +1,7 @@
 """Runs the five BASELINE.json configs on the GPU box and prints the results table of BASELINE.md §5
 (markdown) plus one JSON object per config.  Usage (on a B200 box, from the repo root):
 
-    python tools/run_configs.py [--out profiles/r01_results.md] [--skip-cfg5-full]
+    python tools/run_configs.py [--out profiles/r02_results.md] [--skip-cfg5-full]
 
 configs 1-2 go through the reference-facing host API (pgb_pfile_output_vcf: CPU selection + header +
 GPU export to a file) on real pfile triples written to a tmp dir; their CPU column is the oracle's
@@ -134,7 +134,7 @@ def cfg5_full():
     st = torch.cuda.current_stream().cuda_stream
     for a in range(0, m, blk):
         k = min(blk, m - a)
-        assert pgb200.lib.pgb_dev_synth_records(dev.data_ptr(), R, 5, a, k, n, st) == 0
+        assert pgb200.lib.pgb_dev_synth_records_fast(dev.data_ptr(), R, 5, a, k, n, st) == 0
         image[12 + a * R:12 + (a + k) * R].copy_(dev[:k * R])
     torch.cuda.synchronize()
     del dev
@@ -179,7 +179,7 @@ def main():
         if not a.skip_cli:
             res.append(cfg3_cli(td, orc))
     for name, wl in (("3 chr22 keep-all", "chr22"), ("4 chr22 gather", "gather"), ("5 biobank block", "biobank-block")):
-        d = bench(wl, () if wl == "chr22" else ("--no-file",))
+        d = bench(wl, ("--no-config5",) if wl == "chr22" else ("--no-file", "--no-config5"))
         d["config_name"] = name
         res.append(d)
     if not a.skip_cfg5_full:
