@@ -693,6 +693,7 @@ def run_b200(args, wl, rank, world, local_rank):
     # host-side ceilings, measured in this run on all ranks at once (the host side is shared)
     cal = d2h_calibration(torch, d_out, h_out, total, barrier)
     d2h_gbs = cal["peak"]
+    agg_d2h = sum_over_ranks(d2h_gbs)
     n_thr = max(1, min(16, (os.cpu_count() or 2) // max(1, world)))
     barrier()
     host_fill_gbs = host_write_probe(h_out.numpy(), n_thr)
@@ -723,7 +724,9 @@ def run_b200(args, wl, rank, world, local_rank):
                             "peak_source": "max of {one cudaMemcpyAsync of the whole body, the export's own pattern without kernels "
                                            "(128 MiB chunks over 3 streams)} device->pinned host, all ranks concurrently, measured in this run",
                             "whole_body_gbs": cal["whole_body_gbs"], "chunked_3_streams_128MiB_gbs": cal["chunked_3_streams_128MiB_gbs"],
-                            "aggregate_peak_gbs_all_gpus": sum_over_ranks(d2h_gbs),
+                            "aggregate_peak_gbs_all_gpus": agg_d2h,
+                            "aggregate_achieved_gbs_all_gpus": world * total * args.steps / e2e_s / 1e9,
+                            "frac_of_aggregate_peak": world * total * args.steps / e2e_s / 1e9 / agg_d2h,
                             "host_memory_fill_gbs": host_fill_gbs, "host_memory_fill_threads": n_thr,
                             "host_memory_fill_note": "CPU threads of this rank filling the same page-locked buffer, all ranks at once"}}
         # parity spot check of the e2e result against the device-resident one (first/last 1 MiB)
