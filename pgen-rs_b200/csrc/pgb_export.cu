@@ -781,8 +781,14 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
     if (sam_idx && n_sam == f->N && n_sam > 0 && sam_idx[n_sam - 1] == f->N - 1) sam_idx = nullptr;
     if (!var_idx && n_var > f->M) { pgb_set_error("n_var %llu > variants in file %u", (unsigned long long)n_var, f->M); return PGB_E_RANGE; }
     uint64_t total_pfx = 0;
+    // the planner below places chunk boundaries by binary search when rows (and, in rows mode, row offsets) ascend —
+    // what filter_metadata produces (pfile.rs:319,331); anything else gets the linear scan
+    bool ascending = true;
+    uint32_t maxp_all = 0;
     for (uint64_t i = 0; i < n_var; i++) {
         const uint64_t v = var_idx ? var_idx[i] : i;
+        if (i && var_idx && var_idx[i] <= var_idx[i - 1]) ascending = false;
+        if (i && rows_mode && pfx.row_off[i] < pfx.row_off[i - 1] + pfx.row_len[i - 1]) ascending = false;
         if (v >= f->M && f->standard) {
             pgb_set_error("variant row %llu outside the %u variants of the file", (unsigned long long)v, f->M);
             return PGB_E_RANGE;
@@ -800,6 +806,7 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
             pgb_set_error("prefix_off must be ascending");
             return PGB_E_ARG;
         }
+        maxp_all = std::max(maxp_all, (uint32_t)(prefix_off[i + 1] - prefix_off[i]));
     }
     if (n_var) total_pfx = prefix_off[n_var] - prefix_off[0];
     if (total_pfx && !prefix_blob && !rows_mode) return PGB_E_ARG;
@@ -861,6 +868,24 @@ int export_impl(pgb_file *f, const uint32_t *var_idx, uint64_t n_var, const uint
             uint64_t omin = f->rec_off(var_idx ? var_idx[line] : line), omax = omin;
             uint32_t maxp = (uint32_t)(prefix_off[line + 1] - prefix_off[line]);
             uint64_t tmin = rows_mode ? pfx.row_off[line] : 0, tmax = rows_mode ? pfx.row_off[line] + pfx.row_len[line] : 0;
+            if (ascending && !env_u64("PGB_PLAN_LINEAR", 0)) {
+                // every limit is monotonic in the chunk end: largest b with [line, b) inside all of them
+                auto fits = [&](uint64_t e) { // e > line
+                    if (out_before(e) - out_before(line) > chunk_out) return false;
+                    if ((e - line) * (uint64_t)R > chunk_in) return false;
+                    const uint64_t o = f->rec_off(var_idx ? var_idx[e - 1] : e - 1);
+                    return f->standard || (o - omin) / (R ? R : 1) < 0xffffffffull;
+                };
+                uint64_t lo = line + 1, hi = end; // fits(lo) by definition (a chunk holds at least one line)
+                while (lo < hi) {
+                    const uint64_t mid = lo + (hi - lo + 1) / 2;
+                    if (fits(mid)) lo = mid; else hi = mid - 1;
+                }
+                b = lo;
+                omax = f->rec_off(var_idx ? var_idx[b - 1] : b - 1);
+                maxp = maxp_all; // the export's largest prefix: only sizes tiles / shared memory
+                if (rows_mode) tmax = std::max(tmax, pfx.row_off[b - 1] + pfx.row_len[b - 1]);
+            } else
             while (b < end) {
                 const uint64_t ob = out_before(b + 1) - out_before(line);
                 if (ob > chunk_out) break;

@@ -656,3 +656,42 @@ def test_prefixes_built_on_the_device_from_raw_pvar_rows(pgb, monkeypatch):
         with pytest.raises(pgb.PgbError) as ei:
             pgb.export_rows_to_bytes(f, [0], None, tx, np.array([len(text) - 2], np.uint64), np.array([5], np.uint32))
         assert ei.value.status == pgb.E_RANGE
+
+
+def test_chunk_planner_binary_search_equals_linear_scan(pgb, monkeypatch):
+    """Ascending selections (what filter_metadata produces) get their chunk boundaries by binary search; the chunks
+    and the bytes must be the ones of the linear scan, for keep-all, subsets, both prefix modes and both chunk limits."""
+    rng = np.random.default_rng(321)
+    n, m = 777, 20000
+    recs = rng.integers(0, 256, size=(m, synth.record_size(n)), dtype=np.uint8)
+    rows = [bytes(rng.integers(33, 127, size=int(rng.integers(1, 120)), dtype=np.uint8)) for _ in range(m)]
+    text = b"#h\n"
+    off = np.zeros(m, np.uint64)
+    for i, r in enumerate(rows):
+        off[i] = len(text)
+        text += r + b"\n"
+    ln = np.array([len(r) for r in rows], np.uint32)
+    tx = np.frombuffer(text, dtype=np.uint8)
+    sam = np.sort(rng.choice(n, size=90, replace=False)).astype(np.uint32)
+    with pgb.PgenFile(image=image_of(recs, n)) as f:
+        for env in ({"PGB_CHUNK_MB": "2"}, {"PGB_CHUNK_MB": "64", "PGB_CHUNK_IN_MB": "1"}):
+            for var in (np.arange(m, dtype=np.uint32), np.sort(rng.choice(m, size=m // 3, replace=False)).astype(np.uint32)):
+                pre = [rows[v] + b"\tGT" for v in var]
+                blob = np.frombuffer(b"".join(pre) + b"\0", dtype=np.uint8).copy()
+                poff = np.zeros(len(var) + 1, np.uint64)
+                poff[1:] = np.cumsum([len(x) for x in pre])
+                for sel in (None, sam):
+                    want = onp.format_body(recs, var, np.arange(n) if sel is None else sel, pre)
+                    res = {}
+                    for linear in ("0", "1"):
+                        for k, v in env.items():
+                            monkeypatch.setenv(k, v)
+                        monkeypatch.setenv("PGB_PLAN_LINEAR", linear)
+                        out = np.empty(len(want), np.uint8)
+                        nb, st = f.export_gt_vcf_mem(var, sel, blob, poff, out.ctypes.data, len(want))
+                        assert out.tobytes() == want
+                        assert pgb.export_rows_to_bytes(f, var, sel, tx, off[var], ln[var]) == want
+                        res[linear] = int(st.n_chunks)
+                    assert res["0"] == res["1"] and res["0"] > 3, (env, len(var), res)
+                for k in env:
+                    monkeypatch.delenv(k)
