@@ -673,6 +673,7 @@ def test_chunk_planner_binary_search_equals_linear_scan(pgb, monkeypatch):
     ln = np.array([len(r) for r in rows], np.uint32)
     tx = np.frombuffer(text, dtype=np.uint8)
     sam = np.sort(rng.choice(n, size=90, replace=False)).astype(np.uint32)
+    most = 0
     with pgb.PgenFile(image=image_of(recs, n)) as f:
         for env in ({"PGB_CHUNK_MB": "2"}, {"PGB_CHUNK_MB": "64", "PGB_CHUNK_IN_MB": "1"}):
             for var in (np.arange(m, dtype=np.uint32), np.sort(rng.choice(m, size=m // 3, replace=False)).astype(np.uint32)):
@@ -692,6 +693,8 @@ def test_chunk_planner_binary_search_equals_linear_scan(pgb, monkeypatch):
                         assert out.tobytes() == want
                         assert pgb.export_rows_to_bytes(f, var, sel, tx, off[var], ln[var]) == want
                         res[linear] = int(st.n_chunks)
-                    assert res["0"] == res["1"] and res["0"] > 3, (env, len(var), res)
+                    assert res["0"] == res["1"], (env, len(var), res)
+                    most = max(most, res["0"])
                 for k in env:
                     monkeypatch.delenv(k)
+    assert most > 8
