@@ -248,7 +248,10 @@ int pgb_dev_index_lines_ex(const uint32_t *var_row, const uint64_t *rec_off, uin
 /* K2, general form.  record_bytes = ceil(2 * n_samples / 8) of the file (needed to size the shared-memory
  * staging of the batch path when kidx is non-NULL; 0 = unknown => per-line path).  `suffix`: suffix_len
  * (0..4) bytes, little-endian, written after the prefix_blob bytes of every line — "\tGT" (0x0054 4709,
- * length 3) turns a raw .pvar row into the line prefix of src/pfile.rs:157-161 on the device. */
+ * length 3) turns a raw .pvar row into the line prefix of src/pfile.rs:157-161 on the device.
+ * The batch path fetches records and prefixes with bulk copies of whole 16-byte blocks: besides the 16 readable
+ * bytes after the last record, the 16-byte blocks containing the first and the last byte of every prefix must be
+ * readable (true for any pointer into a cudaMalloc allocation that does not end inside the last block). */
 int pgb_dev_format_lines_ex(const uint8_t *records, uint32_t record_bytes, const pgb_line_meta *meta, uint64_t n_lines,
                             const uint8_t *prefix_blob, uint32_t suffix, uint32_t suffix_len, const uint32_t *kidx,
                             uint32_t n_kept, uint32_t max_prefix_len, uint8_t *out, int variant, void *stream);

@@ -325,6 +325,7 @@ __device__ __forceinline__ void k2b_mbar_wait(uint8_t *mbar, uint32_t parity) {
                      : "=r"(done)
                      : "r"(bar), "r"(parity), "r"(20000u)
                      : "memory");
+        if (!done) __nanosleep(64); // a waiting warp should not compete for issue slots
     } while (!done);
 }
 

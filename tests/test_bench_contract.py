@@ -28,3 +28,27 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                         "--warmup", "0"], capture_output=True, text=True, env=env, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_host_side_ceiling_probes_run_without_a_gpu(tmp_path):
+    """The host-side ceilings bench.py measures (raw sink strategies, CPU fill of the output buffer) are plain
+    host code: exercise them on a small buffer so a broken probe cannot hide until a GPU run."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    import bench
+    buf = np.full(8 << 20, 49, np.uint8)
+    rates = bench.file_sink_ceilings(str(tmp_path / "probe.bin"), memoryview(buf), 4)
+    assert set(rates) == {"buffered_pwrite_1", "buffered_pwrite_4", "o_direct_pwrite_4", "mmap_copy_4"}
+    assert all(isinstance(v, float) and v > 0 for k, v in rates.items() if "o_direct" not in k)
+    assert not (tmp_path / "probe.bin").exists()
+    assert bench.host_write_probe(buf, 2) > 0
+
+
+def test_config5_partition_covers_the_matrix_once():
+    """Strong scaling of configs[4]: rank r owns variants [r*M/N, (r+1)*M/N) — contiguous, disjoint, complete."""
+    m = 200_000
+    for world in (1, 2, 3, 4, 8):
+        ranges = [(r * m // world, (r + 1) * m // world) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == m
+        assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
