@@ -698,3 +698,25 @@ def test_chunk_planner_binary_search_equals_linear_scan(pgb, monkeypatch):
                 for k in env:
                     monkeypatch.delenv(k)
     assert most > 8
+
+
+@pytest.mark.parametrize("variant", [0, 0x10020000, 0x20020000, 0x40020000])
+def test_batch_kernel_many_batches_per_cta(pgb, variant, monkeypatch):
+    """The persistent batch kernel (k2_batch.cuh) cycling its shared-memory stages many times per CTA: tens of
+    thousands of short lines with ragged prefixes; kept-sample counts on both sides of the register-plan limit
+    (ceil(K/4) <= 64) and of one compaction round (32 bytes); keep-all short lines.  Every byte against the oracle."""
+    monkeypatch.setenv("PGB_K2_VARIANT", str(variant))
+    rng = np.random.default_rng(variant + 17)
+    for n, k, m in ((2504, 97, 40000), (2504, 250, 30000), (2504, 300, 30000), (1000, 700, 12000), (300, None, 50000),
+                    (64, None, 60000)):
+        recs = rng.integers(0, 256, size=(m, synth.record_size(n)), dtype=np.uint8)
+        lens = rng.integers(0, 81, size=m)
+        pool = rng.integers(33, 127, size=int(lens.sum()) + 1, dtype=np.uint8)
+        off = np.zeros(m + 1, np.uint64)
+        off[1:] = np.cumsum(lens)
+        pre = [pool[int(off[i]):int(off[i + 1])].tobytes() for i in range(m)]
+        sam = None if k is None else np.sort(rng.choice(n, size=k, replace=False)).astype(np.uint32)
+        with pgb.PgenFile(image=image_of(recs, n)) as f:
+            got = pgb.export_to_bytes(f, None, sam, pool, off)
+        want = onp.format_body(recs, np.arange(m), np.arange(n) if sam is None else sam, pre)
+        assert sha(got) == sha(want), (variant, n, k, m)
