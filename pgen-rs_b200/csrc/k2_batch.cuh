@@ -6,25 +6,25 @@
 //
 // What it replaces: the same loop body as k2_core.cuh (/root/reference/src/pfile.rs:156-192),
 // organised the way BASELINE.json's north_star (b)+(c) describes it.  The kernel is persistent
-// (CTA c takes batches c, c + gridDim, ...) and software-pipelined over two shared-memory stages:
-//   1. INPUT, one batch ahead: thread l hands the 16-byte-aligned covering ranges of line l's
-//      record (records + rec_off: pfile.rs:165-170 as a TMA transfer) and of its prefix bytes to
-//      the bulk-copy engine (cp.async.bulk.shared.global, completion on the stage's mbarrier);
-//      the pgb_line_meta of the batch after that is already in registers, so neither the index
-//      read nor the record read is ever waited for in the steady state;
-//   2. GATHER (pfile.rs:171-175): the kept samples of each staged record are compacted into a
-//      packed 2-bit "virtual record" of ceil(K/4) bytes.  One thread per OUTPUT byte; the
-//      thread's four source positions (byte offset, bit shift) come from the K0 index list and
-//      stay in registers for the whole kernel — 4 LDS.U8 + shift/mask per byte, no warp
-//      reductions;
-//   3. FORMAT (pfile.rs:177-190): the keep-all chunk body runs on the virtual record and writes
-//      the text with 16-byte shared-memory stores into an image of the batch's output bytes
-//      (lines are back to back in the VCF, so a batch is ONE contiguous byte range); prefixes,
-//      the <= 15 + 15 GT bytes around each line's aligned body and the newlines are byte stores
-//      — into shared memory, not global;
-//   4. OUTPUT: the 16-byte-aligned interior of the image leaves with ONE bulk async store
-//      (cp.async.bulk.global.shared::cta) that drains while the next batch is formatted into the
-//      other image; the <= 15 bytes on either end are byte stores.
+// (CTA c takes batches c, c + gridDim, ...), warp-specialised and software-pipelined over two or
+// three shared-memory input stages (pgb_kernels.cu: k2_batch_kernel):
+//   1. INPUT (producer warp, one lane per line of the batch): the pgb_line_meta of the next batch
+//      is already in registers; the lane writes the stage's line table and hands the
+//      16-byte-aligned covering range of its record (records + rec_off: pfile.rs:165-170 as a TMA
+//      transfer) and the batch's prefix bytes to the bulk-copy engine (cp.async.bulk.shared.global,
+//      completion on the stage's `full` mbarrier);
+//   2. GATHER (consumer warps, a warp per line; pfile.rs:171-175): the kept samples of the staged
+//      record are compacted into a packed 2-bit "virtual record" of ceil(K/4) bytes.  One lane per
+//      OUTPUT byte; the lane's four source positions (byte offset, bit shift) come from the K0
+//      index list and stay in registers (or shared memory) for the whole kernel — 4 LDS.U8 +
+//      shift/mask per byte, no warp reductions;
+//   3. FORMAT (pfile.rs:177-190): the keep-all chunk body runs on the virtual record, two 16-byte
+//      chunks per lane and iteration;
+//   4. OUTPUT: either straight to global memory (16-byte .cs stores for the aligned chunks, byte
+//      stores for prefixes, newlines and the <= 15 + 15 ragged GT bytes of a line), or into an
+//      image of the warp's contiguous output range in shared memory that leaves with ONE bulk
+//      async store per warp and batch (cp.async.bulk.global.shared::cta; the <= 15 bytes on either
+//      end are byte stores).  The consumer warps never wait for one another.
 // Every output byte still has exactly one writer and no padding is emitted.
 //
 // Text decode uses a 16-entry table (a nibble = two genotypes -> 8 bytes of text, 128 bytes
@@ -57,7 +57,6 @@ struct pgb_k2b_params {
     uint32_t sfx;      // bytes appended to every prefix after its blob bytes (little-endian), e.g. "\tGT"
     uint32_t sfx_len;  // 0..4; pfx_len includes it
     uint32_t kidx_vec; // kidx is 16-byte aligned
-    uint32_t store_mode; // 0 bulk async store, 1 16-byte st.global by all threads (A/B comparisons)
     uint32_t images;     // 0: no image — the consumer warps store to global memory directly; 1: an image per warp,
                          // bulk-stored (the warp waits for the drain before the next batch); 2: two images per warp
     uint32_t stages;     // input stages (records, prefixes, table): 2 or 3

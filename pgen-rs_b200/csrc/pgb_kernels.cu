@@ -454,17 +454,10 @@ __global__ void __launch_bounds__(K2B_THREADS, 3) k2_batch_kernel(const pgb_k2b_
             const uint8_t *outb = smem + L.outb(img);
             if (ws != 0xFFFFFFFFu) {
                 const uint32_t h0 = (ws + 15u) & ~15u, h1 = we & ~15u;
-                if (p.store_mode == 0) {
-                    if (lane == 0 && h0 < h1)
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g_al + h0),
-                                     "r"(k2b_smem_addr(outb + h0)), "r"(h1 - h0)
-                                     : "memory");
-                } else {
-                    for (uint32_t a = h0 + 16u * lane; a < h1; a += 512u) {
-                        const uint4 v = *reinterpret_cast<const uint4 *>(outb + a);
-                        pgb_st16(g_al + a, v.x, v.y, v.z, v.w, 1);
-                    }
-                }
+                if (lane == 0 && h0 < h1)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g_al + h0),
+                                 "r"(k2b_smem_addr(outb + h0)), "r"(h1 - h0)
+                                 : "memory");
                 k2b_store_edges(g_al, outb, ws, we, lane);
             }
             // one group per batch (possibly empty), so that wait_group.read 1 means "batch n-2 has left"
@@ -713,7 +706,6 @@ static bool plan_k2_batch(uint32_t K, uint32_t R, bool gather, uint32_t max_pref
     bp->vcap = (uint32_t)vcap;
     bp->wcap = images ? (uint32_t)((k2b_lines_per_warp((uint32_t)B) * max_line + 32ull + 127ull) & ~127ull) : 0u;
     bp->outcap = K2B_WARPS * bp->wcap;
-    bp->store_mode = 0;
     bp->images = (uint32_t)images;
     bp->stages = (uint32_t)stages;
     *smem_bytes = pgb_k2b_smem_layout(bp->B, bp->rowcap, bp->pcap, bp->vcap, bp->outcap, gather, bp->images, bp->stages).total;

@@ -69,7 +69,6 @@ extern "C" int sim_format_lines_batch(const uint8_t *records, uint64_t pitch, ui
     p.sfx = sfx;
     p.sfx_len = sfx_len;
     p.kidx_vec = (flags & 1) ? 1u : 0u;
-    p.store_mode = 0;
     p.stages = (flags & 8) ? 3u : 2u;
     const pgb_k2b_layout L = pgb_k2b_smem_layout(p.B, p.rowcap, p.pcap, p.vcap, p.outcap, gather, p.images, p.stages);
     std::vector<uint8_t> smem_store(L.total + 256);
