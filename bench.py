@@ -293,7 +293,8 @@ def d2h_calibration(torch, d_out, h_out, total, barrier):
     h_out[:total].copy_(d_out[:total], non_blocking=True)
     cb.record()
     torch.cuda.synchronize()
-    whole = total / (ca.elapsed_time(cb) * 1e-3) / 1e9
+    whole_s = ca.elapsed_time(cb) * 1e-3
+    whole = total / whole_s / 1e9
     streams = [torch.cuda.Stream() for _ in range(3)]
     chunk = 128 << 20
     barrier()
@@ -303,8 +304,10 @@ def d2h_calibration(torch, d_out, h_out, total, barrier):
         with torch.cuda.stream(streams[i % 3]):
             h_out[a:b].copy_(d_out[a:b], non_blocking=True)
     torch.cuda.synchronize()
-    chunked = total / (time.perf_counter() - t0) / 1e9
-    return {"whole_body_gbs": whole, "chunked_3_streams_128MiB_gbs": chunked, "peak": max(whole, chunked)}
+    chunked_s = time.perf_counter() - t0
+    chunked = total / chunked_s / 1e9
+    return {"whole_body_gbs": whole, "chunked_3_streams_128MiB_gbs": chunked, "peak": max(whole, chunked),
+            "whole_body_s": whole_s, "chunked_s": chunked_s}
 
 
 def file_sink_ceilings(path, mv, n_threads):
@@ -693,7 +696,9 @@ def run_b200(args, wl, rank, world, local_rank):
     # host-side ceilings, measured in this run on all ranks at once (the host side is shared)
     cal = d2h_calibration(torch, d_out, h_out, total, barrier)
     d2h_gbs = cal["peak"]
-    agg_d2h = sum_over_ranks(d2h_gbs)
+    # aggregate ceiling of the box: all ranks' bytes over the time of the SLOWEST rank (summing per-rank rates would
+    # credit the ranks that finish early with bandwidth the others were not yet using)
+    agg_d2h = max(world * total / max_over_ranks(cal["whole_body_s"]), world * total / max_over_ranks(cal["chunked_s"])) / 1e9
     n_thr = max(1, min(16, (os.cpu_count() or 2) // max(1, world)))
     barrier()
     host_fill_gbs = host_write_probe(h_out.numpy(), n_thr)
@@ -725,6 +730,7 @@ def run_b200(args, wl, rank, world, local_rank):
                                            "(128 MiB chunks over 3 streams)} device->pinned host, all ranks concurrently, measured in this run",
                             "whole_body_gbs": cal["whole_body_gbs"], "chunked_3_streams_128MiB_gbs": cal["chunked_3_streams_128MiB_gbs"],
                             "aggregate_peak_gbs_all_gpus": agg_d2h,
+                            "aggregate_peak_source": "all ranks' bytes / slowest rank's time, max over the two copy patterns",
                             "aggregate_achieved_gbs_all_gpus": world * total * args.steps / e2e_s / 1e9,
                             "frac_of_aggregate_peak": world * total * args.steps / e2e_s / 1e9 / agg_d2h,
                             "host_memory_fill_gbs": host_fill_gbs, "host_memory_fill_threads": n_thr,
