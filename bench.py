@@ -22,7 +22,8 @@ Multi-GPU (torchrun): rank r owns the contiguous variant range [r*M, (r+1)*M) of
 (N_gpus*M)-variant matrix — weak scaling, no data-path collective (NCCL only for the timing
 barrier and the max-over-ranks reduction).
 
-Every line also carries `config5`: BASELINE.json configs[4] (500 000 samples x 200 000 variants, 400 GB of
+The default line also carries `other_workloads` (device-resident K1 + K2 of the gather, random1 and biobank-block
+shapes: the rooflines of the kernels chr22 does not exercise) and `config5`: BASELINE.json configs[4] (500 000 samples x 200 000 variants, 400 GB of
 VCF) in STRONG scaling — rank r formats the contiguous variant range [r*200000/N, (r+1)*200000/N), records resident
 in HBM, output ring-buffered — plus one call of the product's own multi-device sharding
 (pgb_export_gt_vcf_mem(devices=[0..N-1]) from rank 0) on a slice of that matrix that crosses the 4 GiB record
@@ -531,6 +532,83 @@ def sharded_call(args, torch, pgb200, lib, dev, world, n, R, L, width, seed):
             "checked_against": "K1+K2 device-resident on device 0, every byte", "setup_s": setup_s}
 
 
+
+def device_resident_line(args, torch, pgb200, lib, dev, rank, barrier, max_over_ranks, name):
+    """Device-resident K1 + K2 of another workload (same method as the main one: W warm-up steps, then `steps` timed
+    steps, CUDA events on the launching stream, max over ranks): the roofline of the kernels the default workload
+    does not exercise (the shared-memory batch kernel on the gather-heavy and short-line shapes)."""
+    wl = WORKLOADS[name]
+    n, m, width, seed = wl["n"], wl["m"], wl["width"], wl["seed"]
+    R = synth.record_size(n)
+    row0 = rank * m
+    stream = torch.cuda.current_stream().cuda_stream
+    recs = torch.zeros(m * R + 64, dtype=torch.uint8, device=dev)
+    pgb200._check(lib.pgb_dev_synth_records_fast(recs.data_ptr(), R, seed, row0, m, n, stream), "synth")
+    if wl["mk"] is None:
+        var, n_lines = None, m
+        blob_np, off_np = synth.uniform_prefix_blob(m, row0, width)
+    else:
+        var = synth.subset_indices(42, m, wl["mk"])
+        n_lines = len(var)
+        b, _ = synth.uniform_prefix_blob(m, row0, width)
+        blob_np = np.ascontiguousarray(b.reshape(m, width)[var]).reshape(-1)
+        off_np = np.arange(n_lines + 1, dtype=np.uint64) * np.uint64(width)
+    sam = None if wl["k"] is None else synth.subset_indices(41, n, wl["k"])
+    K = n if sam is None else len(sam)
+    total = int(off_np[-1]) + n_lines * (4 * K + 1)
+    d_blob = torch.from_numpy(blob_np).to(dev)
+    d_off = torch.from_numpy(off_np.view(np.int64)).to(dev)
+    d_rows = None if var is None else torch.from_numpy(var.view(np.int32)).to(dev)
+    d_kidx = None
+    if sam is not None:
+        mask = np.zeros(4 * R, np.uint8)
+        mask[sam] = 1
+        d_mask = torch.from_numpy(mask).to(dev)
+        d_kidx = torch.zeros(4 * R + 8, dtype=torch.int32, device=dev)
+        d_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        pgb200._check(lib.pgb_dev_compact_samples(d_mask.data_ptr(), 4 * R, d_kidx.data_ptr(), d_cnt.data_ptr(), stream), "K0")
+        assert int(d_cnt.item()) == K
+    d_meta = torch.zeros((n_lines + 1) * 4, dtype=torch.int64, device=dev)
+    d_scr = torch.zeros(lib.pgb_dev_index_scratch_bytes(n_lines) // 8 + 1, dtype=torch.int64, device=dev)
+    d_out = torch.empty(total + 1024, dtype=torch.uint8, device=dev)
+    variant = int(os.environ.get("PGB_K2_VARIANT", "0"), 0)
+
+    def k1():
+        pgb200._check(lib.pgb_dev_index_lines(None if d_rows is None else d_rows.data_ptr(), d_off.data_ptr(), 0, n_lines,
+                                              K, R, d_meta.data_ptr(), d_scr.data_ptr(), stream), "K1")
+
+    def k2():
+        pgb200._check(lib.pgb_dev_format_lines_ex(recs.data_ptr(), R, d_meta.data_ptr(), n_lines, d_blob.data_ptr(), 0, 0,
+                                                  None if d_kidx is None else d_kidx.data_ptr(), K, width, d_out.data_ptr(),
+                                                  variant, stream), "K2")
+
+    for _ in range(args.warmup):
+        k1(); k2()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev0.record()
+    for a, b in evs:
+        k1()
+        a.record()
+        k2()
+        b.record()
+    ev1.record()
+    barrier()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    k2_ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+    alg = n_lines * ((R if sam is None else min(R, 32 * len(np.unique(sam // 128)))) + width + (width + 4 * K + 1))
+    peak, _ = peaks()
+    # the first and the last line against what the kernel's inputs say (prefix bytes and the newline)
+    L = width + 4 * K + 1
+    ok = bytes(d_out[:width].cpu().numpy()) == bytes(blob_np[:width]) and int(d_out[total - 1].item()) == 10 and \
+        bytes(d_out[total - L:total - L + width].cpu().numpy()) == bytes(blob_np[-width:])
+    return {"workload": name, "description": wl["desc"], "kept_samples": K, "kept_variants_per_gpu": n_lines,
+            "value": n_lines * K * args.steps / (dev_ms * 1e-3), "unit": UNIT + " per GPU", "ms_per_step": dev_ms / args.steps,
+            "kernel": "k2_batch_kernel" if (sam is not None or width + 4 * K + 1 <= 3072) else "k2_format_kernel",
+            "kernel_ms": k2_ms, "algorithmic_bytes_per_launch": int(alg), "achieved_gbs": alg / (k2_ms * 1e-3) / 1e9,
+            "frac_of_measured_hbm_peak": alg / (k2_ms * 1e-3) / 1e9 / peak, "first_last_line_ok": ok}
+
 # ------------------------------------------------------------------------ GPU arm ---
 def run_b200(args, wl, rank, world, local_rank):
     import torch
@@ -810,6 +888,13 @@ def run_b200(args, wl, rank, world, local_rank):
                                                            if od["roofline"]["o_direct_ceiling_gbs_all_ranks"] else None))
     clocks = sampler.stop() if sampler else None
 
+    # ---- the other BASELINE shapes, device-resident (the kernels the default workload does not exercise) ----
+    other = None
+    if args.workload == "chr22" and not args.no_other:
+        other = [device_resident_line(args, torch, pgb200, lib, dev, rank, barrier, max_over_ranks, w)
+                 for w in ("gather", "random1", "biobank-block")]
+        torch.cuda.empty_cache()
+
     # ---- configs[4] (biobank shape), strong scaling + the product's own multi-device call ----
     config5 = None
     if not args.no_config5:
@@ -843,7 +928,7 @@ def run_b200(args, wl, rank, world, local_rank):
                          "kernel_ms": k2_ms,
                          "algorithmic_bytes_per_launch": int(alg_bytes), "peak_source": peak_src,
                          "frac_of_nominal_8TBs": achieved / 8000.0, "store_only_ceiling_gbs": fill_gbs},
-            "e2e": e2e, "e2e_file": e2e_file, "e2e_file_disk": e2e_file_disk, "config5": config5, "cpu_baseline": cpu, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+            "e2e": e2e, "e2e_file": e2e_file, "e2e_file_disk": e2e_file_disk, "other_workloads": other, "config5": config5, "cpu_baseline": cpu, "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -863,6 +948,7 @@ def main():
     ap.add_argument("--n-variants", type=int, default=0, help="kernel development: override the workload's variant count")
     ap.add_argument("--no-e2e", action="store_true", help="kernel development: device-resident part only, short line")
     ap.add_argument("--no-config5", action="store_true", help="skip the configs[4] strong-scaling leg")
+    ap.add_argument("--no-other", action="store_true", help="skip the device-resident lines of the other BASELINE shapes")
     ap.add_argument("--config5-variants", type=int, default=0, help="development: shrink configs[4] to this many variants")
     ap.add_argument("--config5-slice", type=int, default=0, help="variants of the slice given to the multi-device call (default 16384)")
     args = ap.parse_args()

@@ -179,7 +179,7 @@ def main():
         if not a.skip_cli:
             res.append(cfg3_cli(td, orc))
     for name, wl in (("3 chr22 keep-all", "chr22"), ("4 chr22 gather", "gather"), ("5 biobank block", "biobank-block")):
-        d = bench(wl, ("--no-config5",) if wl == "chr22" else ("--no-file", "--no-config5"))
+        d = bench(wl, ("--no-config5", "--no-other") if wl == "chr22" else ("--no-file", "--no-config5"))
         d["config_name"] = name
         res.append(d)
     if not a.skip_cfg5_full:
