@@ -720,3 +720,26 @@ def test_batch_kernel_many_batches_per_cta(pgb, variant, monkeypatch):
             got = pgb.export_to_bytes(f, None, sam, pool, off)
         want = onp.format_body(recs, np.arange(m), np.arange(n) if sam is None else sam, pre)
         assert sha(got) == sha(want), (variant, n, k, m)
+
+
+def test_rows_mode_with_rows_longer_than_a_tile(pgb):
+    """On-device prefix construction when a .pvar row (a huge INFO field) spans several K2 tiles: the appended
+    "\\tGT" may straddle a tile boundary."""
+    rng = np.random.default_rng(404)
+    n, m = 301, 8
+    recs = rng.integers(0, 256, size=(m, synth.record_size(n)), dtype=np.uint8)
+    rows = [bytes(rng.integers(33, 127, size=int(sz), dtype=np.uint8))
+            for sz in (16381, 16382, 16383, 16384, 9000, 40000, 32765, 5)]
+    text = b"#h\n"
+    off = np.zeros(m, np.uint64)
+    for i, r in enumerate(rows):
+        off[i] = len(text)
+        text += r + b"\n"
+    ln = np.array([len(r) for r in rows], np.uint32)
+    tx = np.frombuffer(text, dtype=np.uint8)
+    sam = np.sort(rng.choice(n, size=77, replace=False)).astype(np.uint32)
+    with pgb.PgenFile(image=image_of(recs, n)) as f:
+        for sel in (None, sam, np.zeros(0, np.uint32)):
+            got = pgb.export_rows_to_bytes(f, None, sel, tx, off, ln)
+            want = onp.format_body(recs, np.arange(m), np.arange(n) if sel is None else sel, [r + b"\tGT" for r in rows])
+            assert got == want
